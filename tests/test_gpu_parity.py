@@ -1,0 +1,270 @@
+"""GPU tier: the CUDA path, called through the C ABI, against the CPU oracle on the same seeded
+inputs.
+
+Bars (BASELINE.json north_star):
+  * local observation lists: bit-exact (here even in kdtree2's visiting ORDER, and r2 bit-exact);
+  * yo / Yb rows: bit-exact real32;
+  * wbar, Wa, analysis before the real32 cast: relative 1e-10 in FP64, 1e-5 in FP32, compared
+    through the basis-invariant Wa / analysis, never raw eigenvectors;
+  * final real32 field (after cast + RTPP/RTPS in real32): within 4 real32 ulps of the oracle
+    (rel 5e-7); points without local obs bit-identical to the input.
+"""
+import numpy as np
+import pytest
+
+from cwbnwp_letkf_b200 import config as C
+from cwbnwp_letkf_b200 import host as H
+from cwbnwp_letkf_b200 import synthetic as S
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+TOL64 = 1e-10
+TOL32 = 1e-5
+
+
+def _engines(sc, real64=True):
+    eng = H.LetkfB200(sc.k, real64)
+    orc = O.Oracle(sc.k, real64)
+    for o in sc.obs.values():
+        eng.set_obs(o)
+        orc.set_obs(o)
+    return eng, orc
+
+
+def _relerr(a, b):
+    scale = np.maximum(np.abs(b).max(), 1e-300)
+    return np.abs(a - b).max() / scale
+
+
+# ------------------------------------------------------------------------------ search
+@pytest.mark.parametrize("var", ["T", "QRAIN", "P"])
+def test_local_obs_lists_bit_exact(var):
+    sc, rng = S.scenario_tiny(k=8)
+    cfg = C.sample_namelist(var)
+    eng, orc = _engines(sc)
+    got = eng.get_lz(cfg, sc.xyz_grid)
+    ntrees = orc.build_tree(cfg)
+    assert len(got) == ntrees > 0
+    truncated = 0
+    for pt in range(sc.npts):
+        ref = orc.get_lz(sc.xyz_grid[pt])
+        for t, (fam, typ, idx, r2) in enumerate(ref):
+            gf, gt, cnt, gidx, gr2 = got[t]
+            assert (gf, gt) == (fam, typ)
+            assert cnt[pt] == len(idx)
+            assert np.array_equal(gidx[pt, :cnt[pt]], idx)
+            assert np.array_equal(gr2[pt, :cnt[pt]].view(np.int32), r2.view(np.int32))
+            tc = [x for x in cfg.types if x.family == fam and x.type == typ][0]
+            truncated += int(len(idx) == tc.max_lz_pts)
+    assert truncated > 0, "case must exercise max_lz_pts truncation"
+
+
+def test_search_large_radar_sorted_index_sets():
+    """Config-M-like density on a sub-domain: sorted index sets equal (the north-star criterion)."""
+    rng = np.random.default_rng(5)
+    sc = S.Scenario("sub", 24, 24, 10, 8, 2000.0, S.make_grid(24, 24, 10, 2000.0))
+    S.add_radar(sc, rng, 60000, 40000, n_sites=2, radius=40e3)
+    cfg = C.sample_namelist("QRAIN", use_gts=False)
+    eng, orc = _engines(sc)
+    got = eng.get_lz(cfg, sc.xyz_grid)
+    orc.build_tree(cfg)
+    pts = rng.choice(sc.npts, 400, replace=False)
+    full = 0
+    for pt in pts:
+        (fam, typ, idx, r2), = orc.get_lz(sc.xyz_grid[pt])
+        _, _, cnt, gidx, _ = got[0]
+        assert np.array_equal(np.sort(gidx[pt, :cnt[pt]]), np.sort(idx))
+        full += int(len(idx) == 300)
+    assert full > 100
+
+
+# ------------------------------------------------------------------------------ yoyb
+@pytest.mark.parametrize("var,wf", [("T", 0), ("QRAIN", 0), ("T", 1)])
+def test_yoyb_rows_bit_exact(var, wf):
+    sc, rng = S.scenario_tiny(k=8)
+    cfg = C.sample_namelist(var, weight_function=wf)
+    eng, orc = _engines(sc)
+    off, yo, yb = eng.letkf_yoyb(cfg, sc.xyz_grid)
+    orc.build_tree(cfg)
+    nonempty = 0
+    for pt in range(0, sc.npts, 3):
+        ryo, ryb = orc.letkf_yoyb(sc.xyz_grid[pt])
+        a, b = off[pt], off[pt + 1]
+        assert b - a == len(ryo)
+        if len(ryo):
+            nonempty += 1
+            assert np.array_equal(yo[a:b].view(np.int32), ryo.view(np.int32))     # NaNs compare by bits
+            assert np.array_equal(yb[a:b].view(np.int32), ryb.view(np.int32))
+    assert nonempty > 20
+
+
+# ------------------------------------------------------------------------------ weights / analysis
+def _weights_case(sc, cfg, real64, tol, npick=60, seed=1):
+    eng, orc = _engines(sc, real64)
+    rng = np.random.default_rng(seed)
+    xb = S.make_field(rng, sc.k, sc.xyz_grid, 280.0, 5.0, 1.0)
+    p, wbar, Wa, raw = eng.letkf_weights(cfg, sc.xyz_grid, xb)
+    orc.build_tree(cfg)
+    inflat = np.float32(sc.k - 1) / np.float32(cfg.multi_infl)
+    cand = np.nonzero(p > 0)[0]
+    assert len(cand) > 10
+    worst = 0.0
+    for pt in rng.choice(cand, min(npick, len(cand)), replace=False):
+        yo, yb = orc.letkf_yoyb(sc.xyz_grid[pt])
+        assert len(yo) == p[pt]
+        xa, rw, rWa, rraw = orc.letkf_solve(xb[:, pt], yo, yb, inflat)
+        e1, e2, e3 = _relerr(wbar[pt], rw), _relerr(Wa[pt], rWa), _relerr(raw[pt], rraw)
+        worst = max(worst, e1, e2, e3)
+        assert e1 < tol and e2 < tol and e3 < tol, (pt, e1, e2, e3)
+    # points without obs report zero weights
+    z = np.nonzero(p == 0)[0]
+    if len(z):
+        assert not wbar[z].any() and not Wa[z].any()
+    return worst
+
+
+@pytest.mark.parametrize("k", [8, 32, 40, 96])
+def test_weights_and_raw_analysis_fp64(k):
+    sc, _ = S.scenario_tiny(k=k)
+    _weights_case(sc, C.sample_namelist("T"), True, TOL64)
+
+
+def test_weights_fp64_qrain_and_2d():
+    sc, _ = S.scenario_tiny(k=32)
+    _weights_case(sc, C.sample_namelist("QRAIN"), True, TOL64)
+    _weights_case(sc, C.sample_namelist("P"), True, TOL64)
+
+
+def test_weights_fp32_build():
+    sc, _ = S.scenario_tiny(k=32)
+    _weights_case(sc, C.sample_namelist("T"), False, TOL32)
+
+
+def test_weights_k256():
+    sc, _ = S.scenario_tiny(k=256, nx=6, ny=5, nz=4)
+    _weights_case(sc, C.sample_namelist("QRAIN"), True, TOL64, npick=12)
+
+
+@pytest.mark.parametrize("var,real64", [("T", True), ("QRAIN", True), ("P", True), ("T", False)])
+def test_analysis_field_matches_oracle(var, real64):
+    sc, rng = S.scenario_tiny(k=32)
+    cfg = C.sample_namelist(var)
+    cfg.tune_q = False
+    eng, orc = _engines(sc, real64)
+    f = np.stack([S.make_field(rng, sc.k, sc.xyz_grid, 280.0, 5.0, 1.0),
+                  S.make_field(rng, sc.k, sc.xyz_grid, 5.0, 3.0, 2.0)])
+    ref = f.copy()
+    npo, rows = orc.analyze(cfg, sc.xyz_grid, ref, nthreads=4)
+    got = f.copy()
+    st = eng.analyze(cfg, sc.xyz_grid, got)
+    assert st.npts == sc.npts and st.npts_analysed == npo and st.rows == rows
+    changed = (ref != f).any(axis=(0, 1))
+    assert np.array_equal(got[:, :, ~changed], f[:, :, ~changed])          # untouched points: bit-identical
+    tol = 5e-7 if real64 else 2e-4
+    scale = np.abs(ref).max(axis=1, keepdims=True)
+    assert (np.abs(got - ref) <= tol * scale).all()
+    if real64:                                                             # almost every value is bit-equal
+        assert (got == ref).mean() > 0.98
+
+
+def test_analysis_with_tune_q_and_gaspari_cohn_nan_parity():
+    sc, rng = S.scenario_tiny(k=16)
+    cfg = C.sample_namelist("QRAIN", weight_function=1)                    # GC: real32 NaNs near the cutoff (Q7)
+    eng, orc = _engines(sc)
+    f = S.make_field(rng, sc.k, sc.xyz_grid, 1e-3, 1e-3, 5e-4)
+    ref = f.copy()
+    orc.analyze(cfg, sc.xyz_grid, ref, nthreads=4)
+    O.tune_q(ref)
+    got = f.copy()
+    eng.analyze(cfg, sc.xyz_grid, got)                                     # cfg.tune_q is set for QRAIN
+    nan_ref = np.isnan(ref).any(0)
+    nan_got = np.isnan(got).any(0)
+    assert np.array_equal(nan_ref, nan_got)
+    ok = ~nan_ref
+    scale = np.abs(ref[:, ok]).max()
+    assert np.abs(got[:, ok] - ref[:, ok]).max() <= 5e-7 * scale
+
+
+def test_tune_q_bit_exact():
+    rng = np.random.default_rng(0)
+    q = rng.normal(0, 1e-3, (32, 5000)).astype(np.float32)
+    q[:, :10] = 0.0                                                         # 0/0 -> NaN like the reference
+    q[:, 10:20] = -np.abs(q[:, 10:20])
+    ref = q.copy()
+    O.tune_q(ref)
+    eng = H.LetkfB200(32)
+    got = q.copy()
+    eng.tune_q(got)
+    assert np.array_equal(got.view(np.int32), ref.view(np.int32))
+
+
+def test_no_active_type_leaves_field_untouched():
+    sc, rng = S.scenario_tiny(k=8)
+    cfg = C.sample_namelist("QRAIN", use_radar=False)                       # GTS hclr = -1 for QRAIN
+    eng, _ = _engines(sc)
+    f = S.make_field(rng, sc.k, sc.xyz_grid, 1.0, 1.0, 1.0)
+    got = f.copy()
+    st = eng.analyze(cfg, sc.xyz_grid, got)
+    assert st.ntrees == 0 and st.npts_analysed == 0 and np.array_equal(got, f)
+
+
+def test_mixed_dimension_family_is_refused_like_the_oracle():
+    sc, rng = S.scenario_tiny(k=8)
+    S.add_gts(sc, rng, 0, 0, 0, 0, 0, n_gpspw=10)
+    eng, _ = _engines(sc)
+    with pytest.raises(H.LetkfError, match="2-D and 3-D"):
+        eng.get_lz(C.sample_namelist("T", use_gpspw=True), sc.xyz_grid)
+
+
+def test_chunking_is_invisible():
+    sc, rng = S.scenario_tiny(k=8)
+    cfg = C.sample_namelist("T")
+    eng, _ = _engines(sc)
+    f = S.make_field(rng, sc.k, sc.xyz_grid, 280.0, 5.0, 1.0)
+    a = f.copy()
+    eng.analyze(cfg, sc.xyz_grid, a)
+    eng.set_chunk(97)
+    b = f.copy()
+    eng.analyze(cfg, sc.xyz_grid, b)
+    assert np.array_equal(a, b)
+
+
+# ------------------------------------------------------------------------------ eigensolver
+def _letkf_like(rng, b, k, p, dtype):
+    Y = rng.normal(size=(b, k, p))
+    Y -= Y.mean(1, keepdims=True)
+    s = np.exp(-0.25 * rng.uniform(0, 13.33, (b, 1, p))) / rng.uniform(0.5, 2.5, (b, 1, p))
+    Y = Y * s
+    return ((k - 1) / 1.1 * np.eye(k) + Y @ Y.transpose(0, 2, 1)).astype(dtype)
+
+
+@pytest.mark.parametrize("k", [2, 8, 32, 33, 64, 128, 256])
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_syevd_batched_against_lapack(k, dtype):
+    rng = np.random.default_rng(k)
+    b = 24 if k <= 64 else 6
+    eps = np.finfo(dtype).eps
+    for family in ("letkf", "goe"):
+        if family == "letkf":
+            A = _letkf_like(rng, b, k, 300, dtype)
+        else:
+            G = rng.normal(size=(b, k, k))
+            A = ((G + G.transpose(0, 2, 1)) / 2).astype(dtype)
+        eng = H.LetkfB200(max(k, 2), dtype == np.float64)
+        W, V, sweeps = eng.syevd_batched(A)
+        Wl, Vl = O.syevd_batch(A, nthreads=4)
+        assert 1 <= sweeps <= 30
+        for i in range(b):
+            a64 = A[i].astype(np.float64)
+            nrm = np.abs(a64).sum(1).max()
+            v = V[i].T.astype(np.float64)                                   # columns = eigenvectors
+            assert np.abs(W[i] - Wl[i]).max() <= 40 * k * eps * nrm
+            assert (np.diff(W[i]) >= 0).all()
+            assert np.abs(a64 @ v - v * W[i].astype(np.float64)).max() <= 60 * k * eps * nrm
+            assert np.abs(v.T @ v - np.eye(k)).max() <= 60 * k * eps
+            if family == "letkf":                                           # basis-invariant f(A) = A^(-1/2)
+                vl = Vl[i].T.astype(np.float64)
+                f_gpu = (v / np.sqrt(W[i].astype(np.float64))) @ v.T
+                f_ref = (vl / np.sqrt(Wl[i].astype(np.float64))) @ vl.T
+                assert _relerr(f_gpu, f_ref) < (1e-10 if dtype == np.float64 else 1e-4)
