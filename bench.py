@@ -1,0 +1,380 @@
+#!/usr/bin/env python
+"""Benchmark of the LETKF local-analysis hot path (BASELINE.json metric: analysed grid points/s).
+
+A *step* is one pass of the hot path -- the loop body of letkf_driver for every grid point of one
+3-D variable -- over BASELINE config M: 450x450x50 grid, 32 members, ~10^6 radar + ~10^4 GTS
+observations, variable `T` (GTS + radial velocity, the heaviest localisation mix of input.nml).
+
+  value        : swept grid points/s with grid + ensemble resident in HBM (letkf_b200_analyze_dev),
+                 timed with CUDA events on the library's stream, max over ranks.
+  e2e          : same metric through the host-pointer C-ABI call (letkf_b200_analyze) with pinned
+                 HOST buffers; H2D of xyz+ensemble and D2H of the analysis inside the timed region.
+  roofline     : dominant kernel (the batched eigensolver) against the FP64 FMA peak measured by
+                 the committed micro-benchmark (letkf_b200_fma_peak); per-stage numbers in `stages`.
+  cpu_baseline : the oracle (a port of the reference algorithm; the Fortran reference cannot be
+                 compiled here) on the host cores over a bounded sample of the same workload.
+
+`--impl reference` times that CPU restatement alone.  N > 1 (torchrun): grid columns are
+partitioned cyclically across ranks as in module_mpi_util.f90:73-188, observations replicated with
+the member-sliced NCCL all-gather that mirrors module_gts_omboma.f90:601-605; strong scaling.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+VAR = os.environ.get("LETKF_BENCH_VAR", "T")
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--members", type=int, default=32)
+    ap.add_argument("--nx", type=int, default=450)
+    ap.add_argument("--ny", type=int, default=450)
+    ap.add_argument("--nz", type=int, default=50)
+    ap.add_argument("--var", default=VAR)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                pw.append(float(r[3]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"),
+                                   r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_baseline(sc, cfg, seconds: float, threads: int):
+    """Oracle (port of the reference hot path) on the host cores over a bounded random sample of the
+    workload's grid points, full observation set.  Returns points/s and what the sample was."""
+    from oracle import oracle as O
+    orc = O.Oracle(sc.k, True)
+    for o in sc.obs.values():
+        orc.set_obs(o)
+    rng = np.random.default_rng(11)
+    from cwbnwp_letkf_b200 import synthetic as S
+
+    def run(n):
+        sel = np.sort(rng.choice(sc.npts, n, replace=False))
+        xyz = np.ascontiguousarray(sc.xyz_grid[sel])
+        f = S.make_field(rng, sc.k, xyz, 280.0, 5.0, 1.0)
+        orc.build_tree(cfg)                       # build time excluded, like the GPU tree cache
+        t0 = time.perf_counter()
+        from oracle.oracle import lib, to_c, _p
+        import ctypes
+        npo, rows = ctypes.c_int64(0), ctypes.c_int64(0)
+        rc = lib().or_analyze(ctypes.c_void_p(orc.h), ctypes.byref(orc.ccfg), ctypes.c_int64(n), _p(xyz), 1,
+                              _p(f), threads, ctypes.byref(npo), ctypes.byref(rows))
+        dt = time.perf_counter() - t0
+        assert rc == 0
+        return dt, npo.value, rows.value
+
+    pilot = min(2000, sc.npts)
+    dt, _, _ = run(pilot)
+    n = int(min(sc.npts, max(pilot, pilot * seconds / max(dt, 1e-3))))
+    dt, npo, rows = run(n)
+    return {"value": n / dt, "unit": "grid points/s", "cores": threads, "kind": "port",
+            "sample": f"{n} random grid points of the {sc.nx}x{sc.ny}x{sc.nz} grid, full obs set, variable {cfg_name(cfg)}, "
+                      f"{npo} analysed, {rows / max(npo, 1):.0f} rows/point, {dt:.1f} s; oracle = C++ port of the "
+                      "reference loop with OpenBLAS dsyrk/dsyevd/dgemm, one OpenMP thread per core",
+            "seconds": dt}
+
+
+def cfg_name(cfg):
+    return getattr(cfg, "_name", "?")
+
+
+def main():
+    a = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    from cwbnwp_letkf_b200 import config as C
+    from cwbnwp_letkf_b200 import synthetic as S
+
+    cfg = C.sample_namelist(a.var)
+    cfg.tune_q = False if a.var == "T" else cfg.tune_q
+    cfg._name = a.var
+    workload = f"M: {a.nx}x{a.ny}x{a.nz} grid, dx=2km, k={a.members}, variable {a.var}"
+    config = {"workload": workload, "members": a.members, "variable": a.var,
+              "namelist": "input.nml (hclr/vclr/max_lz_pts/inflation/RTPP/RTPS as shipped)",
+              "l2": "inputs larger than L2 (ensemble field %.2f GB)" % (a.nx * a.ny * a.nz * a.members * 4 / 1e9),
+              "partition": "1 GPU" if world == 1 else f"columns cyclic over {world} ranks, obs replicated"}
+
+    if a.impl == "reference":
+        if rank != 0:
+            return
+        sc, rng = S.scenario_M(k=a.members, nx=a.nx, ny=a.ny, nz=a.nz)
+        threads = os.cpu_count() or 1
+        vals = []
+        per_step = max(2.0, min(a.cpu_seconds, 60.0 / max(a.steps + a.warmup, 1)))
+        last = None
+        for i in range(a.warmup + a.steps):
+            last = cpu_baseline(sc, cfg, per_step, threads)
+            if i >= a.warmup:
+                vals.append(last["value"])
+        v = float(np.mean(vals))
+        out = {"impl": "reference", "metric": "analysed grid points/s", "value": v, "unit": "grid points/s",
+               "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+               "ms_per_step": 1e3 * (a.nx * a.ny * a.nz) / v, "higher_is_better": True, "scaling": "strong",
+               "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+               "cpu_baseline": {"value": v, "unit": "grid points/s", "cores": threads, "kind": "port",
+                                "sample": last["sample"]},
+               "e2e": {"value": v, "unit": "grid points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+               "note": "the Fortran/MPI reference cannot be compiled in this image (no Fortran compiler, MPI, "
+                       "NetCDF, SSL2); this arm times the C++ port (oracle/) on a bounded sample, ms_per_step "
+                       "is the extrapolation to the full grid"}
+        print(json.dumps(out))
+        return
+
+    import torch
+    import torch.distributed as dist
+    from cwbnwp_letkf_b200 import host as H
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+
+    # ---- synthetic workload (same seed on every rank) ----
+    sc, rng = S.scenario_M(k=a.members, nx=a.nx, ny=a.ny, nz=a.nz)
+    k = sc.k
+    eng = H.LetkfB200(k, True, local_rank)
+
+    # ---- observations: member-sliced all-gather of H(x), like mpi_iallgatherv (gts:601-605, rad:179) ----
+    t_obs0 = time.perf_counter()
+    for key, o in sc.obs.items():
+        if world == 1:
+            eng.set_obs(o)
+            continue
+        n, nv = o.n, o.nvar
+        lo, hi = rank * k // world, (rank + 1) * k // world
+        assert k % world == 0
+        mine = torch.from_numpy(np.ascontiguousarray(o.hdxb[lo:hi])).to(dev)      # this rank "read" members lo:hi
+        full = torch.empty((k, n, nv), dtype=torch.float32, device=dev)
+        dist.all_gather_into_tensor(full, mine)
+        qc = None
+        if o.qc is not None:
+            mq = torch.from_numpy(np.ascontiguousarray(o.qc[lo:hi])).to(dev)
+            qc = torch.empty((k, n, nv), dtype=torch.int32, device=dev)
+            dist.all_gather_into_tensor(qc, mq)
+        xyz = torch.from_numpy(o.xyz).to(dev)
+        obs = torch.from_numpy(o.obs).to(dev)
+        err = None if o.error is None else torch.from_numpy(o.error).to(dev)
+        torch.cuda.synchronize()
+        eng.set_obs_dev(o.family, o.type, n, nv, xyz, obs, err, full, qc)
+        del full, qc, mine
+    torch.cuda.synchronize()
+    t_obs = time.perf_counter() - t_obs0
+
+    # ---- this rank's columns (cyclic, module_mpi_util.f90:80-127) ----
+    ncol = sc.nx * sc.ny
+    cols = np.arange(rank, ncol, world)
+    pts = (cols[None, :] + ncol * np.arange(sc.nz)[:, None]).reshape(-1)
+    xyz_local = np.ascontiguousarray(sc.xyz_grid[pts]) if world > 1 else sc.xyz_grid
+    npts_local = xyz_local.shape[0]
+    total_pts = sc.npts
+    frng = np.random.default_rng(1234 + rank)
+    field0 = S.make_field(frng, k, xyz_local, 280.0, 5.0, 1.0)                      # var[k, npts_local]
+
+    d_xyz = torch.from_numpy(xyz_local).to(dev)
+    d_field0 = torch.from_numpy(field0).to(dev)
+    d_var = torch.empty_like(d_field0)
+    ccfg = C.to_c(cfg)
+    stream = torch.cuda.ExternalStream(eng.stream_ptr, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def dev_step():
+        d_var.copy_(d_field0)                # restore the background (not timed: outside the events)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        st = eng.analyze_ptr(ccfg, npts_local, d_xyz.data_ptr(), 1, d_var.data_ptr(), dev=True)
+        e1.record(stream)
+        e1.synchronize()
+        return e0.elapsed_time(e1), st
+
+    # FP64 / FP32 FMA peaks (roofline denominators the driver does not measure)
+    fma64 = eng.fma_peak(0)
+    fma32 = eng.fma_peak(1)
+
+    for _ in range(a.warmup):
+        dev_step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = eng.launch_count
+    t_steps, stats = [], None
+    barrier()
+    wall0 = time.perf_counter()
+    for _ in range(a.steps):
+        ms, stats = dev_step()
+        t_steps.append(ms)
+    barrier()
+    wall = time.perf_counter() - wall0
+    launches = eng.launch_count - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    ms_local = float(np.sum(t_steps))
+    if world > 1:
+        t = torch.tensor([ms_local], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+        cnt = torch.tensor([stats.npts_analysed, stats.rows, launches], device=dev, dtype=torch.float64)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+        analysed, rows, launches = int(cnt[0].item()), int(cnt[1].item()), int(cnt[2].item())
+    else:
+        ms_total, analysed, rows = ms_local, stats.npts_analysed, stats.rows
+    ms_per_step = ms_total / a.steps
+    value = total_pts / (ms_per_step * 1e-3)
+
+    # ---- end to end through the host-pointer ABI with pinned host buffers ----
+    e2e = None
+    if not a.no_e2e:
+        h_xyz = torch.from_numpy(xyz_local).pin_memory()
+        h_field0 = torch.from_numpy(field0).pin_memory()
+        h_var = torch.empty_like(h_field0).pin_memory()
+
+        def e2e_step():
+            h_var.copy_(h_field0)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            eng.analyze_ptr(ccfg, npts_local, h_xyz.data_ptr(), 1, h_var.data_ptr(), dev=False)
+            e1.record(stream)
+            e1.synchronize()
+            return e0.elapsed_time(e1)
+
+        e2e_step()
+        barrier()
+        ms_e = float(np.sum([e2e_step() for _ in range(a.steps)]))
+        if world > 1:
+            t = torch.tensor([ms_e], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_e = float(t.item())
+        # the device result equals the resident-path result
+        same = bool(torch.equal(h_var.to(dev), d_var))
+        e2e = {"value": total_pts / (ms_e / a.steps * 1e-3), "unit": "grid points/s",
+               "h2d_bytes_per_step": int(total_pts * (3 + k) * 4),
+               "d2h_bytes_per_step": int(total_pts * k * 4), "ms_per_step": ms_e / a.steps,
+               "matches_resident_path": same}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline (SURVEY.md 8(d) algorithmic counts) from the last timed step of rank 0 ----
+    units = stats.units
+    rows0 = stats.rows
+    ntree_bytes = 12 * stats.npts + 8 * rows0          # xyz in + (idx,r2) written for kept entries (approx: rows ~ entries)
+    stage = {
+        "search": {"ms": stats.ms_search, "bound": "hbm", "achieved": ntree_bytes / (stats.ms_search * 1e-3) / 1e9,
+                   "peak": None, "unit": "GB/s"},
+        "gram": {"ms": stats.ms_gram, "bound": "fp64",
+                 "achieved": (k * (k + 1) + 2 * k) * rows0 / (stats.ms_gram * 1e-3) / 1e12, "peak": fma64,
+                 "unit": "TFLOP/s", "gathered_GBs": (4 * k + 8) * rows0 / (stats.ms_gram * 1e-3) / 1e9},
+        "eigen": {"ms": stats.ms_eigen, "bound": "fp64", "achieved": 4.0 * k**3 * units / (stats.ms_eigen * 1e-3) / 1e12,
+                  "peak": fma64, "unit": "TFLOP/s", "eigensolves_per_s": units / (stats.ms_eigen * 1e-3),
+                  "max_sweeps": stats.max_sweeps},
+        "transform": {"ms": stats.ms_transform, "bound": "hbm",
+                      "achieved": 8.0 * k * units / (stats.ms_transform * 1e-3) / 1e9, "peak": None, "unit": "GB/s"},
+        "tree_build_ms": stats.ms_tree,
+    }
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm = peaks.get("hbm_gbs", 6650.0)
+    for s_ in ("search", "transform"):
+        stage[s_]["peak"] = hbm
+    for s_ in ("search", "gram", "eigen", "transform"):
+        stage[s_]["frac"] = stage[s_]["achieved"] / stage[s_]["peak"] if stage[s_]["ms"] > 0 else None
+    dom = max(("search", "gram", "eigen", "transform"), key=lambda s_: stage[s_]["ms"])
+    roofline = {"kernel": dom, "bound": stage[dom]["bound"], "achieved": stage[dom]["achieved"],
+                "peak": stage[dom]["peak"], "unit": stage[dom]["unit"], "frac": stage[dom]["frac"], "traffic": None,
+                "peak_source": ("letkf_b200_fma_peak micro-benchmark (FP64 FMA, measured in this run)"
+                                if stage[dom]["bound"] == "fp64" else
+                                ("MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s")),
+                "share_of_step": stage[dom]["ms"] / max(stats.ms_total, 1e-9)}
+
+    cpu = None
+    if not a.no_cpu_baseline:
+        cpu = cpu_baseline(sc, cfg, a.cpu_seconds, os.cpu_count() or 1)
+
+    out = {"metric": "analysed grid points/s", "value": value, "unit": "grid points/s", "n_gpus": world,
+           "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+           "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+           "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+           "stages": stage, "points_analysed": int(analysed), "analysed_fraction": analysed / total_pts,
+           "points_per_s_analysed_only": analysed / (ms_per_step * 1e-3), "rows_per_analysed_point": rows / max(analysed, 1),
+           "fma_peak_tflops": {"fp64": fma64, "fp32": fma32}, "obs_setup_s": t_obs, "wall_s_timed": wall,
+           "obs_values": sc.total_obs_values()}
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

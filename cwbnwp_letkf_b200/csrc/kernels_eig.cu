@@ -21,12 +21,12 @@ template <typename T>
 struct Eps;
 template <>
 struct Eps<double> {
-  static __device__ __forceinline__ double tol() { return 1e-15; }
+  static __device__ __forceinline__ double tol(int k) { return 2.220446049250313e-16 * sqrt((double)k); }
   static __device__ __forceinline__ double tiny() { return 1e-290; }
 };
 template <>
 struct Eps<float> {
-  static __device__ __forceinline__ float tol() { return 2e-7f; }
+  static __device__ __forceinline__ float tol(int k) { return 1.1920929e-7f * sqrtf((float)k); }
   static __device__ __forceinline__ float tiny() { return 1e-30f; }
 };
 
@@ -40,12 +40,15 @@ __device__ __forceinline__ T warp_sum(T v) {
 // Cholesky in place on the lower triangle of G (column-major, ld = k), then zero the strict
 // upper triangle.  Whole CTA participates.
 template <typename T>
-__device__ void block_cholesky(T *G, int k) {
+__device__ bool block_cholesky(T *G, int k) {
   const int tid = threadIdx.x, nt = blockDim.x;
   const int warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
+  bool ok = true;  // every thread reads the same pivots, so this is CTA-uniform
   for (int j = 0; j < k; ++j) {
     __syncthreads();
-    const T d = sqrt(G[j + (size_t)j * k]);
+    const T piv = G[j + (size_t)j * k];
+    if (!(piv > T(0))) ok = false;
+    const T d = sqrt(piv);
     __syncthreads();
     if (tid == 0) G[j + (size_t)j * k] = d;
     const T dinv = T(1) / d;
@@ -62,6 +65,7 @@ __device__ void block_cholesky(T *G, int k) {
     if (i < j) G[e] = T(0);
   }
   __syncthreads();
+  return ok;
 }
 
 // One-sided Jacobi sweeps on the columns of G until every pair is orthogonal to tolerance.
@@ -72,7 +76,7 @@ __device__ int block_jacobi(T *G, int k) {
   const int warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
   const int kk = (k + 1) & ~1;
   const int half = kk / 2, nm1 = kk - 1;
-  const T tol = Eps<T>::tol();
+  const T tol = Eps<T>::tol(k);
   int sweeps = 0;
   for (; sweeps < 60; ++sweeps) {
     int rotated = 0;
@@ -150,47 +154,50 @@ __global__ void __launch_bounds__(256)
     if (SMEM)
       for (int e = tid; e < k * k; e += nt) G[e] = Gg[e];
     if (tid == 0) s_shift = T(0);
+    __syncthreads();
+    block_cholesky(G, k);  // C is SPD by construction; a NaN input propagates
   } else {
     const T *A = Ain + u * (int64_t)k * k;
-    // symmetrise from the lower triangle, Gershgorin lower bound
-    for (int e = tid; e < k * k; e += nt) {
-      const int i = e % k, j = e / k;
-      G[e] = i >= j ? A[i + (size_t)j * k] : A[j + (size_t)i * k];
-    }
-    __syncthreads();
-    T lowest = sizeof(T) == 8 ? T(1e300) : T(3e38);
-    T scale = T(0);
-    for (int i = tid; i < k; i += nt) {
-      T off = 0;
-      for (int j = 0; j < k; ++j)
-        if (j != i) off += fabs(G[i + (size_t)j * k]);
-      lowest = min(lowest, G[i + (size_t)i * k] - off);
-      scale = max(scale, fabs(G[i + (size_t)i * k]) + off);
-    }
-    // block reduce through shared memory (k <= 256 = blockDim)
     __shared__ T red_lo[256], red_sc[256];
-    red_lo[tid] = lowest;
-    red_sc[tid] = scale;
-    __syncthreads();
-    for (int o = 128; o > 0; o >>= 1) {
-      if (tid < o) {
-        red_lo[tid] = min(red_lo[tid], red_lo[tid + o]);
-        red_sc[tid] = max(red_sc[tid], red_sc[tid + o]);
-      }
+    // First try the matrix as it is (an SPD input keeps its full relative accuracy); if a pivot
+    // fails, shift by a Gershgorin bound so that it becomes definite and factor again.
+    for (int attempt = 0; attempt < 2; ++attempt) {
       __syncthreads();
+      for (int e = tid; e < k * k; e += nt) {  // symmetrise from the lower triangle
+        const int i = e % k, j = e / k;
+        G[e] = i >= j ? A[i + (size_t)j * k] : A[j + (size_t)i * k];
+      }
+      if (tid == 0 && attempt == 0) s_shift = T(0);
+      __syncthreads();
+      if (attempt == 1) {
+        T lowest = sizeof(T) == 8 ? T(1e300) : T(3e38);
+        T scale = T(0);
+        for (int i = tid; i < k; i += nt) {
+          T off = 0;
+          for (int j = 0; j < k; ++j)
+            if (j != i) off += fabs(G[i + (size_t)j * k]);
+          lowest = min(lowest, G[i + (size_t)i * k] - off);
+          scale = max(scale, fabs(G[i + (size_t)i * k]) + off);
+        }
+        red_lo[tid] = lowest;
+        red_sc[tid] = scale;
+        __syncthreads();
+        for (int o = 128; o > 0; o >>= 1) {
+          if (tid < o) {
+            red_lo[tid] = min(red_lo[tid], red_lo[tid + o]);
+            red_sc[tid] = max(red_sc[tid], red_sc[tid + o]);
+          }
+          __syncthreads();
+        }
+        if (tid == 0) s_shift = red_sc[0] * T(1e-3) - min(red_lo[0], T(0));
+        __syncthreads();
+        const T sh = s_shift;
+        for (int i = tid; i < k; i += nt) G[i + (size_t)i * k] += sh;
+        __syncthreads();
+      }
+      if (block_cholesky(G, k)) break;
     }
-    if (tid == 0) {
-      const T lo = red_lo[0], sc = red_sc[0];
-      // shift only when the Gershgorin discs do not already prove definiteness
-      s_shift = lo > sc * T(1e-3) ? T(0) : (sc * T(1e-3) - lo);
-    }
-    __syncthreads();
-    const T sh = s_shift;
-    for (int i = tid; i < k; i += nt) G[i + (size_t)i * k] += sh;
   }
-  __syncthreads();
-
-  block_cholesky(G, k);
   const int sweeps = block_jacobi(G, k);
   if (tid == 0 && sweeps_max) atomicMax(sweeps_max, sweeps);
 
