@@ -13,7 +13,7 @@ CSRC = os.path.join(HERE, "csrc")
 BUILD = os.path.join(HERE, "_build")
 LIB = os.path.join(BUILD, "libletkf_b200.so")
 SOURCES = ["api.cu", "kdtree_host.cu", "kernels_obs.cu", "kernels_search.cu", "kernels_gram.cu",
-           "kernels_eig.cu", "kernels_xform.cu"]
+           "kernels_eig.cu", "kernels_xform.cu", "kernels_eig32.cu", "kernels_k32.cu"]
 HEADERS = [os.path.join(CSRC, "letkf_internal.cuh"),
            os.path.join(HERE, "..", "include", "letkf_b200.h"),
            os.path.join(HERE, "..", "include", "letkf_b200_math.h")]

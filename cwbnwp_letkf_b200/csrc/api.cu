@@ -33,6 +33,7 @@ struct letkf_b200_ctx {
   cudaEvent_t ev[8] = {};
   std::map<std::pair<int, int>, std::unique_ptr<ObsDev>> obs;  // (family, type), iteration = reference order
   int64_t chunk_override = 0;
+  bool force_generic = false;  // LETKF_B200_GENERIC=1: use the generic block-per-unit kernels for every k
   // per-call device staging for the host-pointer entry points
   DevBuf<float> d_xyz, d_var;
   // per-chunk scratch
@@ -74,6 +75,8 @@ extern "C" int letkf_b200_init(letkf_b200_ctx **out, int nmember, int real64, in
     c->k = nmember;
     c->real64 = real64 != 0;
     c->device = device;
+    const char *fg = getenv("LETKF_B200_GENERIC");
+    c->force_generic = fg && fg[0] == '1';
     LK_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     for (auto &ev : c->ev) LK_CUDA(cudaEventCreate(&ev));
     *out = c.release();
@@ -375,17 +378,34 @@ static void run_pipeline(letkf_b200_ctx *c, const letkf_b200_var_config *cfg, in
         c->wbar.ensure((size_t)nunits * k * sizeof(T));
         T *C = reinterpret_cast<T *>(c->C.p), *b = reinterpret_cast<T *>(c->b.p);
         T *lam = reinterpret_cast<T *>(c->lam.p), *wbar = reinterpret_cast<T *>(c->wbar.p);
-        launch_gram<T>(s, tv, k, nunits, c->unit_pt.p, mu, C, b, c->nanflag.p);
+        const bool fast32 = k == 32 && !c->force_generic;  // warp-per-unit register kernels
+        if (fast32 && sizeof(T) == 8)
+          launch_gram32(s, tv, nunits, c->unit_pt.p, (double)mu, reinterpret_cast<double *>(C),
+                        reinterpret_cast<double *>(b), c->nanflag.p);
+        else
+          launch_gram<T>(s, tv, k, nunits, c->unit_pt.p, mu, C, b, c->nanflag.p);
         LK_CUDA(cudaEventRecord(c->ev[4], s));
-        launch_eig_solve<T>(s, k, nunits, C, b, lam, wbar, c->counters.p + 1);
+        if (fast32)
+          launch_eig32_solve<T>(s, nunits, C, b, lam, wbar, c->counters.p + 1);
+        else
+          launch_eig_solve<T>(s, k, nunits, C, b, lam, wbar, c->counters.p + 1);
         LK_CUDA(cudaEventRecord(c->ev[5], s));
-        if (co.wbar || co.Wa)
-          launch_weights_dump<T>(s, k, nunits, c->unit_pt.p, C, lam, wbar,
-                                 co.wbar ? co.wbar + c0 * k : nullptr,
-                                 co.Wa ? co.Wa + c0 * (int64_t)k * k : nullptr);
-        if (co.transform && nfields > 0)
-          launch_transform<T>(s, k, nunits, c->unit_pt.p, npts, c0, C, lam, wbar, c->nanflag.p, nfields, d_var,
-                              cfg->use_rtpp, cfg->rtpp_alpha, cfg->use_rtps, cfg->rtps_alpha, co.xa_raw);
+        if (co.wbar || co.Wa) {
+          double *wo = co.wbar ? co.wbar + c0 * k : nullptr;
+          double *Wo = co.Wa ? co.Wa + c0 * (int64_t)k * k : nullptr;
+          if (fast32)
+            launch_weights_dump32<T>(s, nunits, c->unit_pt.p, C, lam, wbar, wo, Wo);
+          else
+            launch_weights_dump<T>(s, k, nunits, c->unit_pt.p, C, lam, wbar, wo, Wo);
+        }
+        if (co.transform && nfields > 0) {
+          if (fast32)
+            launch_transform32<T>(s, nunits, c->unit_pt.p, npts, c0, C, lam, wbar, c->nanflag.p, nfields, d_var,
+                                  cfg->use_rtpp, cfg->rtpp_alpha, cfg->use_rtps, cfg->rtps_alpha, co.xa_raw);
+          else
+            launch_transform<T>(s, k, nunits, c->unit_pt.p, npts, c0, C, lam, wbar, c->nanflag.p, nfields, d_var,
+                                cfg->use_rtpp, cfg->rtpp_alpha, cfg->use_rtps, cfg->rtps_alpha, co.xa_raw);
+        }
         LK_CUDA(cudaEventRecord(c->ev[6], s));
         LK_CUDA(cudaEventSynchronize(c->ev[6]));
         float ms = 0;
@@ -616,7 +636,10 @@ template <typename T>
 static void syevd_dev(letkf_b200_ctx *c, int k, int64_t batch, const void *A, void *W, void *V, int32_t *sweeps) {
   c->counters.ensure(4);
   LK_CUDA(cudaMemsetAsync(c->counters.p, 0, 4 * sizeof(int32_t), c->stream));
-  launch_syevd<T>(c->stream, k, batch, (const T *)A, (T *)W, (T *)V, c->counters.p + 1);
+  if (k == 32 && !c->force_generic)
+    launch_syevd32<T>(c->stream, batch, (const T *)A, (T *)W, (T *)V, c->counters.p + 1);
+  else
+    launch_syevd<T>(c->stream, k, batch, (const T *)A, (T *)W, (T *)V, c->counters.p + 1);
   if (sweeps) {
     LK_CUDA(cudaMemcpyAsync(sweeps, c->counters.p + 1, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
     LK_CUDA(cudaStreamSynchronize(c->stream));

@@ -1,0 +1,336 @@
+// k = 32 eigensolver: one warp per matrix, the whole factor in registers.
+//
+// Same method as kernels_eig.cu (Cholesky C = L L^T, one-sided Jacobi on the columns of L), laid out
+// for a warp: lane i owns ROW i of the factor in 32 registers, so a column rotation
+// (g_p, g_q) <- (c g_p - s g_q, s g_p + c g_q) is purely lane-local with compile-time register
+// indices.  Only the pair inner products cross lanes: the 16 products of a round-robin step are
+// summed with one transposed butterfly (16 shuffled doubles, not 16 x 5), after which lanes 2n
+// and 2n+1 both hold gamma_n and compute the rotation of pair n.  Column norms are carried along
+// with the rotation update formulas (alpha - t gamma, beta + t gamma) and refreshed exactly once
+// per sweep; (c, s) reach every lane through a 256-byte shared-memory broadcast.  Pairs are always
+// the register pairs (2n, 2n+1): after every step the registers are permuted by the fixed
+// round-robin rotation (31 steps return to the identity), so the step body is one small loop and
+// stays in the instruction cache.
+//
+// Double-precision sqrt / divide in the rotation are replaced by MUFU seeds + Newton steps
+// (2 iterations: full double accuracy); exact orthogonality only needs c^2 + s^2 = 1, which
+// c = rsqrt(1 + t^2), s = c t delivers.
+#include "letkf_internal.cuh"
+
+namespace lk {
+
+constexpr int K32 = 32;
+constexpr unsigned FULL = 0xffffffffu;
+
+template <typename T>
+struct Fast;
+template <>
+struct Fast<double> {
+  static __device__ __forceinline__ double rsqrt(double x) {  // x > 0 within float range
+    double r = (double)rsqrtf((float)x);
+    const double h = 0.5 * x;
+    double e = fma(-h * r, r, 0.5);
+    r = fma(r, e, r);
+    e = fma(-h * r, r, 0.5);
+    r = fma(r, e, r);
+    return r;
+  }
+  static __device__ __forceinline__ double rcp(double x) {
+    float rf;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rf) : "f"((float)x));
+    double r = (double)rf;
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    return r;
+  }
+  static __device__ __forceinline__ double tol2(int k) { return 4.930380657631324e-32 * k; }  // (eps sqrt k)^2
+};
+template <>
+struct Fast<float> {
+  static __device__ __forceinline__ float rsqrt(float x) {
+    float r = rsqrtf(x);
+    const float h = 0.5f * x;
+    const float e = fmaf(-h * r, r, 0.5f);
+    return fmaf(r, e, r);
+  }
+  static __device__ __forceinline__ float rcp(float x) { return __frcp_rn(x); }
+  static __device__ __forceinline__ float tol2(int k) { return 1.4210855e-14f * k; }
+};
+
+__host__ __device__ constexpr int rr_pos(int m) { return (m & 1) ? 31 - (m >> 1) : (m >> 1); }
+__host__ __device__ constexpr int rr_reg(int p) { return p <= 15 ? 2 * p : 2 * (31 - p) + 1; }
+// register that feeds register m in the round-robin rotation
+__host__ __device__ constexpr int rr_src(int m) {
+  return rr_reg(rr_pos(m) == 0 ? 0 : (rr_pos(m) == 1 ? 31 : rr_pos(m) - 1));
+}
+
+// sum v[0..N) over the warp; afterwards v[0] in lane l is the total of element (l >> (5 - log2 N))
+// -- for N = 16 element l>>1, for N = 32 element l.
+template <typename T, int N>
+__device__ __forceinline__ void transposed_reduce(T (&v)[N], int lane) {
+#pragma unroll
+  for (int n = N, mask = 16; n > 1; n >>= 1, mask >>= 1) {
+    const bool up = lane & mask;
+#pragma unroll
+    for (int i = 0; i < n / 2; ++i) {
+      const T send = up ? v[i] : v[i + n / 2];
+      const T keep = up ? v[i + n / 2] : v[i];
+      v[i] = keep + __shfl_xor_sync(FULL, send, mask);
+    }
+  }
+  if (N == 16) v[0] += __shfl_xor_sync(FULL, v[0], 1);
+}
+
+// Cholesky of the matrix whose row `lane` (entries j <= lane) is in g[]; leaves L there (zeros above
+// the diagonal).  colbuf: 32 T of shared memory private to the warp.  Returns false if a pivot is
+// not positive (warp-uniform).
+template <typename T>
+__device__ __forceinline__ bool warp_cholesky32(T (&g)[K32], int lane, T *colbuf) {
+  bool ok = true;
+#pragma unroll
+  for (int j = 0; j < K32; ++j) {
+    const T piv = __shfl_sync(FULL, g[j], j);
+    ok = ok && (piv > T(0));
+    const T rinv = Fast<T>::rsqrt(piv > T(0) ? piv : T(1));
+    const T l = lane >= j ? g[j] * rinv : T(0);
+    g[j] = l;
+    if (j < K32 - 1) {
+      __syncwarp();
+      colbuf[lane] = l;
+      __syncwarp();
+#pragma unroll
+      for (int m = j + 1; m < K32; ++m) g[m] = fma(-l, colbuf[m], g[m]);
+    }
+  }
+#pragma unroll
+  for (int m = 1; m < K32; ++m)
+    if (m > lane) g[m] = T(0);
+  return ok;
+}
+
+// one-sided Jacobi on the columns held as registers; returns the sweep count
+template <typename T>
+__device__ __forceinline__ int warp_jacobi32(T (&g)[K32], int lane, T *csbuf /* 32 T: (c,s) x 16 */) {
+  const T tol2 = Fast<T>::tol2(K32);
+  // lane that holds, before a rotation step, the norm this lane's register slot receives
+  const int p = (lane & 1) ? 31 - (lane >> 1) : (lane >> 1);
+  const int pp = p == 0 ? 0 : (p == 1 ? 31 : p - 1);
+  const int src_lane = pp <= 15 ? 2 * pp : 2 * (31 - pp) + 1;
+  int sweeps = 0;
+  for (; sweeps < 30; ++sweeps) {
+    // exact squared column norms: lane l <- ||column in register slot l||^2
+    T d;
+    {
+      T sq[K32];
+#pragma unroll
+      for (int j = 0; j < K32; ++j) sq[j] = g[j] * g[j];
+      transposed_reduce<T, K32>(sq, lane);
+      d = sq[0];
+    }
+    int rotated = 0;
+#pragma unroll 1
+    for (int step = 0; step < K32 - 1; ++step) {
+      T gam[16];
+#pragma unroll
+      for (int n = 0; n < 16; ++n) gam[n] = g[2 * n] * g[2 * n + 1];
+      transposed_reduce<T, 16>(gam, lane);
+      const T gamma = gam[0];
+      const T dpart = __shfl_xor_sync(FULL, d, 1);
+      const T alpha = (lane & 1) ? dpart : d;
+      const T beta = (lane & 1) ? d : dpart;
+      const bool rot = gamma * gamma > tol2 * alpha * beta;
+      T c = T(1), s = T(0), t = T(0);
+      {
+        const T delta = beta - alpha;
+        T x = fma(delta, delta, T(4) * gamma * gamma);
+        x = rot ? x : T(1);
+        const T h = x * Fast<T>::rsqrt(x);
+        const T den = fabs(delta) + h;
+        const T tt = (delta >= T(0) ? T(2) : T(-2)) * gamma * Fast<T>::rcp(den);
+        const T cc = Fast<T>::rsqrt(fma(tt, tt, T(1)));
+        if (rot) {
+          t = tt;
+          c = cc;
+          s = cc * tt;
+        }
+      }
+      rotated |= rot;
+      d = (lane & 1) ? fma(t, gamma, d) : fma(-t, gamma, d);  // beta + t gamma | alpha - t gamma
+      __syncwarp();
+      if (!(lane & 1)) {
+        csbuf[lane] = c;      // pair n = lane/2 -> csbuf[2n], csbuf[2n+1]
+        csbuf[lane + 1] = s;
+      }
+      __syncwarp();
+#pragma unroll
+      for (int n = 0; n < 16; ++n) {
+        const T cn = csbuf[2 * n], sn = csbuf[2 * n + 1];
+        const T a = g[2 * n], b = g[2 * n + 1];
+        g[2 * n] = fma(cn, a, -(sn * b));
+        g[2 * n + 1] = fma(sn, a, cn * b);
+      }
+      // round-robin rotation of the register slots and of the norms that travel with them
+      {
+        T ng[K32];
+#pragma unroll
+        for (int m = 0; m < K32; ++m) ng[m] = g[rr_src(m)];
+#pragma unroll
+        for (int m = 0; m < K32; ++m) g[m] = ng[m];
+      }
+      d = __shfl_sync(FULL, d, src_lane);
+    }
+    if (!__any_sync(FULL, rotated)) {
+      ++sweeps;
+      break;
+    }
+  }
+  return sweeps;
+}
+
+// MODE 0: C (row-major lower / symmetric full, SPD), b -> U^T-by-rows (U[i][j] at i*32+j), lam, wbar
+// MODE 1: A (column-major, lower referenced) -> W ascending, V column-major
+template <typename T, int MODE>
+__global__ void __launch_bounds__(128)
+    eig32_warp_kernel(int64_t n, T *__restrict__ Cio, const T *__restrict__ bvec, T *__restrict__ lam,
+                      T *__restrict__ wbar, const T *__restrict__ Ain, T *__restrict__ Wout,
+                      T *__restrict__ Vout, int32_t *__restrict__ sweeps_max) {
+  __shared__ __align__(16) T sbuf[4][64];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int64_t u = (int64_t)blockIdx.x * 4 + w;
+  if (u >= n) return;
+  T *buf = sbuf[w];
+  T g[K32];
+  T shift = T(0), scale = T(1);
+
+  if (MODE == 0) {
+    const T *Cu = Cio + u * (int64_t)(K32 * K32) + (int64_t)lane * K32;
+#pragma unroll
+    for (int j = 0; j < K32; j += 2) {
+      const T x0 = Cu[j], x1 = Cu[j + 1];
+      g[j] = j <= lane ? x0 : T(0);
+      g[j + 1] = j + 1 <= lane ? x1 : T(0);
+    }
+    warp_cholesky32<T>(g, lane, buf);
+  } else {
+    const T *A = Ain + u * (int64_t)(K32 * K32);
+    T full[K32];
+#pragma unroll
+    for (int j = 0; j < K32; ++j) full[j] = j <= lane ? A[lane + j * K32] : A[j + lane * K32];
+    // scale by the largest |diagonal| so that the float seeds of rsqrt/rcp stay in range
+    T dmax = fabs(full[0]);
+#pragma unroll
+    for (int j = 1; j < K32; ++j) dmax = j == lane ? fabs(full[j]) : dmax;
+    dmax = lane == 0 ? fabs(full[0]) : dmax;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) dmax = max(dmax, __shfl_xor_sync(FULL, dmax, o));
+    scale = dmax > T(0) ? dmax : T(1);
+    const T iscale = T(1) / scale;
+#pragma unroll
+    for (int j = 0; j < K32; ++j) full[j] *= iscale;
+#pragma unroll
+    for (int j = 0; j < K32; ++j) g[j] = j <= lane ? full[j] : T(0);
+    if (!warp_cholesky32<T>(g, lane, buf)) {
+      // not positive definite: shift by a Gershgorin bound and factor again
+      T off = T(0), dg = T(0);
+#pragma unroll
+      for (int j = 0; j < K32; ++j) {
+        off += j == lane ? T(0) : fabs(full[j]);
+        dg = j == lane ? full[j] : dg;
+      }
+      T lo = dg - off, sc = fabs(dg) + off;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        lo = min(lo, __shfl_xor_sync(FULL, lo, o));
+        sc = max(sc, __shfl_xor_sync(FULL, sc, o));
+      }
+      shift = sc * T(1e-3) - min(lo, T(0));
+#pragma unroll
+      for (int j = 0; j < K32; ++j) g[j] = j <= lane ? full[j] + (j == lane ? shift : T(0)) : T(0);
+      warp_cholesky32<T>(g, lane, buf);
+    }
+  }
+
+  const int sweeps = warp_jacobi32<T>(g, lane, buf);
+  if (lane == 0 && sweeps_max) atomicMax(sweeps_max, sweeps);
+
+  // eigenvalues = squared column norms (lane j <- lambda_j), eigenvectors = normalised columns
+  T lambda;
+  {
+    T sq[K32];
+#pragma unroll
+    for (int j = 0; j < K32; ++j) sq[j] = g[j] * g[j];
+    transposed_reduce<T, K32>(sq, lane);
+    lambda = sq[0];
+  }
+  __syncwarp();
+  buf[lane] = Fast<T>::rsqrt(lambda);
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < K32; ++j) g[j] *= buf[j];
+
+  if (MODE == 0) {
+    // wbar = U diag(1/lambda) U^T b   (eig:37-76 + core:651-652)
+    const T bi = bvec[u * K32 + lane];
+    T z;
+    {
+      T pr[K32];
+#pragma unroll
+      for (int j = 0; j < K32; ++j) pr[j] = g[j] * bi;
+      transposed_reduce<T, K32>(pr, lane);
+      z = pr[0] / lambda;
+    }
+    __syncwarp();
+    buf[lane] = z;
+    __syncwarp();
+    T wb = T(0);
+#pragma unroll
+    for (int j = 0; j < K32; ++j) wb = fma(g[j], buf[j], wb);
+    T *Uo = Cio + u * (int64_t)(K32 * K32) + (int64_t)lane * K32;
+#pragma unroll
+    for (int j = 0; j < K32; ++j) Uo[j] = g[j];
+    lam[u * K32 + lane] = lambda;
+    wbar[u * K32 + lane] = wb;
+  } else {
+    // ascending order like LAPACK
+    int rank = 0;
+#pragma unroll
+    for (int l = 0; l < K32; ++l) {
+      const T ll = __shfl_sync(FULL, lambda, l);
+      rank += (ll < lambda) || (ll == lambda && l < lane);
+    }
+    Wout[u * K32 + rank] = (lambda - shift) * scale;
+    T *V = Vout + u * (int64_t)(K32 * K32);
+#pragma unroll
+    for (int j = 0; j < K32; ++j) {
+      const int rj = __shfl_sync(FULL, rank, j);
+      V[rj * K32 + lane] = g[j];
+    }
+  }
+}
+
+template <typename T>
+void launch_eig32_solve(cudaStream_t s, int64_t n, T *C_inout_U, const T *b, T *lam, T *wbar,
+                        int32_t *sweeps_max) {
+  if (n == 0) return;
+  eig32_warp_kernel<T, 0><<<(unsigned)((n + 3) / 4), 128, 0, s>>>(n, C_inout_U, b, lam, wbar, nullptr, nullptr,
+                                                                   nullptr, sweeps_max);
+  launch_counter()++;
+  LK_CUDA(cudaGetLastError());
+}
+template <typename T>
+void launch_syevd32(cudaStream_t s, int64_t n, const T *A, T *W, T *V, int32_t *sweeps_max) {
+  if (n == 0) return;
+  eig32_warp_kernel<T, 1><<<(unsigned)((n + 3) / 4), 128, 0, s>>>(n, nullptr, nullptr, nullptr, nullptr, A, W, V,
+                                                                   sweeps_max);
+  launch_counter()++;
+  LK_CUDA(cudaGetLastError());
+}
+template void launch_eig32_solve<double>(cudaStream_t, int64_t, double *, const double *, double *, double *,
+                                         int32_t *);
+template void launch_eig32_solve<float>(cudaStream_t, int64_t, float *, const float *, float *, float *, int32_t *);
+template void launch_syevd32<double>(cudaStream_t, int64_t, const double *, double *, double *, int32_t *);
+template void launch_syevd32<float>(cudaStream_t, int64_t, const float *, float *, float *, int32_t *);
+
+}  // namespace lk

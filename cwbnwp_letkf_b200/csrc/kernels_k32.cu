@@ -1,0 +1,275 @@
+// k = 32 fast paths of the Gram and transform stages (FP64 build): one warp per analysis unit.
+//
+// gram32: C = Yb Yb^T + mu I and b = Yb yo on the FP64 tensor pipe.  C is symmetric, so only the
+// 10 lower 8x8 tiles of the 4x4 tile grid are accumulated: per 4 observation rows one lane loads
+// 4 perturbations (member 8I + lane/4 of row r + lane%4, I = 0..3), forms yb = pert*error_inv in
+// real32 (single rounding, module_letkf_core.f90:452/525), promotes, and the SAME register serves
+// as the A fragment of tile row I and the B fragment of tile column I of
+// mma.sync.m8n8k4.f64 -- 10 DMMA per 4 rows instead of 32 DFMA per row and lane.
+//
+// transform32: xa = xb_mean + xb'.wbar + sqrt(k-1) U Lambda^(-1/2) U^T xb' with lane i holding row i
+// of U (the layout eig32 writes), one transposed butterfly for U^T xb' and a shared-memory
+// broadcast for the second product; RTPP/RTPS exactly as kernels_xform.cu.
+#include "letkf_internal.cuh"
+
+namespace lk {
+
+constexpr unsigned FULLM = 0xffffffffu;
+
+__device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(d0), "+d"(d1)
+               : "d"(a), "d"(b));
+}
+
+__global__ void __launch_bounds__(128)
+    gram32_dmma_kernel(TreeViews tv, int64_t nunits, const int32_t *__restrict__ unit_pt, double mu,
+                       double *__restrict__ C, double *__restrict__ bvec, int32_t *__restrict__ nanflag) {
+  const int lane = threadIdx.x & 31;
+  const int64_t unit = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (unit >= nunits) return;
+  const int64_t q = unit_pt[unit];
+  const int lr = lane >> 2, lc = lane & 3;
+  double acc[10][2];
+#pragma unroll
+  for (int t = 0; t < 10; ++t) acc[t][0] = acc[t][1] = 0.0;
+  double bacc[4] = {0.0, 0.0, 0.0, 0.0};
+  bool anynan = false;
+
+  for (int t = 0; t < tv.ntrees; ++t) {
+    const TreeView &TV = tv.t[t];
+    const int ncand = TV.cnt[q] * TV.nact;
+    for (int c0 = 0; c0 < ncand; c0 += 32) {
+      // candidate (tree entry, slot) c0 + lane -> row metadata
+      bool pass = false;
+      float ei = 0.f, yo = 0.f;
+      const float *pr = TV.pert;
+      const int c = c0 + lane;
+      if (c < ncand) {
+        const int j = c / TV.nact, a = c - j * TV.nact;
+        const int64_t o = (int64_t)(TV.idx[q * TV.nalloc + j] - 1) * TV.nvar + TV.act[a];
+        if (TV.pass[o]) {
+          pass = true;
+          ei = lk_error_inv(TV.err[o], TV.r2[q * TV.nalloc + j], tv.weight_function);
+          yo = LK_MUL(TV.omm[o], ei);
+          pr = TV.pert + o * 32;
+          anynan = anynan || (ei != ei);
+        }
+      }
+      const unsigned pmask = __ballot_sync(FULLM, pass);
+#pragma unroll
+      for (int g8 = 0; g8 < 8; ++g8) {
+        if (((pmask >> (4 * g8)) & 0xFu) == 0u) continue;  // warp-uniform
+        const int src = 4 * g8 + lc;
+        const float e = __shfl_sync(FULLM, ei, src);
+        const float y = __shfl_sync(FULLM, yo, src);
+        const float *p = (const float *)__shfl_sync(FULLM, (unsigned long long)pr, src);
+        const bool ok = (pmask >> src) & 1u;
+        double a[4];
+#pragma unroll
+        for (int I = 0; I < 4; ++I) {
+          const float v = ok ? LK_MUL(__ldg(p + 8 * I + lr), e) : 0.f;
+          a[I] = (double)v;
+        }
+        const double yd = (double)y;
+#pragma unroll
+        for (int I = 0; I < 4; ++I) bacc[I] = fma(a[I], yd, bacc[I]);
+        int tix = 0;
+#pragma unroll
+        for (int I = 0; I < 4; ++I)
+#pragma unroll
+          for (int J = 0; J <= I; ++J) {
+            dmma884(acc[tix][0], acc[tix][1], a[I], a[J]);
+            ++tix;
+          }
+      }
+    }
+  }
+  double *Cu = C + unit * 1024;
+  {
+    int tix = 0;
+#pragma unroll
+    for (int I = 0; I < 4; ++I)
+#pragma unroll
+      for (int J = 0; J <= I; ++J) {
+        const int row = 8 * I + lr, col = 8 * J + 2 * lc;
+        double2 v;
+        v.x = acc[tix][0] + (row == col ? mu : 0.0);
+        v.y = acc[tix][1] + (row == col + 1 ? mu : 0.0);
+        *reinterpret_cast<double2 *>(Cu + row * 32 + col) = v;
+        ++tix;
+      }
+  }
+#pragma unroll
+  for (int I = 0; I < 4; ++I) {
+    double s = bacc[I];
+    s += __shfl_xor_sync(FULLM, s, 1);
+    s += __shfl_xor_sync(FULLM, s, 2);
+    if (lc == 0) bvec[unit * 32 + 8 * I + lr] = s;
+  }
+  const bool wn = __any_sync(FULLM, anynan);
+  if (lane == 0) nanflag[unit] = wn ? 1 : 0;
+}
+
+void launch_gram32(cudaStream_t s, const TreeViews &tv, int64_t nunits, const int32_t *unit_pt, double mu,
+                   double *C, double *b, int32_t *nanflag) {
+  if (nunits == 0) return;
+  gram32_dmma_kernel<<<(unsigned)((nunits + 3) / 4), 128, 0, s>>>(tv, nunits, unit_pt, mu, C, b, nanflag);
+  launch_counter()++;
+  LK_CUDA(cudaGetLastError());
+}
+
+// ---- transform, k = 32 ------------------------------------------------------------------------------
+template <typename T, int N>
+__device__ __forceinline__ void treduce(T (&v)[N], int lane) {
+#pragma unroll
+  for (int n = N, mask = 16; n > 1; n >>= 1, mask >>= 1) {
+    const bool up = lane & mask;
+#pragma unroll
+    for (int i = 0; i < n / 2; ++i) {
+      const T send = up ? v[i] : v[i + n / 2];
+      const T keep = up ? v[i + n / 2] : v[i];
+      v[i] = keep + __shfl_xor_sync(FULLM, send, mask);
+    }
+  }
+}
+
+template <typename T>
+__device__ __forceinline__ T wsum(T v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULLM, v, o);
+  return v;
+}
+
+// sequential (member 0..31) real32 sum of one value per lane, as the oracle defines sum()
+__device__ __forceinline__ float seq_sum32(float v) {
+  float s = 0.f;
+#pragma unroll
+  for (int m = 0; m < 32; ++m) s = LK_ADD(s, __shfl_sync(FULLM, v, m));
+  return s;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(128)
+    transform32_kernel(int64_t nunits, const int32_t *__restrict__ unit_pt, int64_t npts_total, int64_t pt_base,
+                       const T *__restrict__ U, const T *__restrict__ lam, const T *__restrict__ wbar,
+                       const int32_t *__restrict__ nanflag, int nfields, float *__restrict__ var, int use_rtpp,
+                       float rtpp_alpha, int use_rtps, float rtps_alpha, double *__restrict__ xa_raw) {
+  __shared__ __align__(16) T sbuf[4][32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int64_t unit = (int64_t)blockIdx.x * 4 + w;
+  if (unit >= nunits) return;
+  T *buf = sbuf[w];
+  const int64_t pt = pt_base + unit_pt[unit];
+  T u[32];
+  {
+    const T *Uu = U + unit * 1024 + (int64_t)lane * 32;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) u[j] = Uu[j];
+  }
+  const T sk = sqrt((T)31);
+  const T scale = sk / sqrt(lam[unit * 32 + lane]);  // lane j: sqrt(k-1)/sqrt(lambda_j)
+  const T wb = wbar[unit * 32 + lane];
+  const bool isnan_unit = nanflag[unit] != 0;
+  const float ninv = LK_DIV(1.0f, 32.0f);
+
+  for (int f = 0; f < nfields; ++f) {
+    float *v = var + (int64_t)f * npts_total * 32;
+    const float xb = v[(int64_t)lane * npts_total + pt];                 // core:228
+    const T xmean = (T)LK_MUL(seq_sum32(xb), ninv);                       // core:671 (real32)
+    const T xp = (T)xb - xmean;                                           // core:672
+    const T sdot = wsum(xp * wb);
+    T pr[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) pr[j] = u[j] * xp;
+    treduce<T, 32>(pr, lane);                                             // lane j: (U^T xb')_j
+    __syncwarp();
+    buf[lane] = pr[0] * scale;
+    __syncwarp();
+    T y = 0;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) y = fma(u[j], buf[j], y);
+    T xa = xmean + (sdot + y);                                            // core:673-675
+    if (isnan_unit) xa = xa * T(NAN);
+    if (xa_raw) xa_raw[pt * 32 + lane] = (double)xa;
+    float xa32 = (float)xa;                                               // core:679
+    if (use_rtpp || use_rtps) {                                           // core:684-698
+      const float xa_mean = LK_MUL(seq_sum32(xa32), ninv);
+      float xap = LK_SUB(xa32, xa_mean);
+      if (use_rtpp) {
+        const float t1 = LK_MUL(LK_SUB(1.0f, rtpp_alpha), xap);
+        xap = (float)((T)t1 + (T)rtpp_alpha * xp);
+      }
+      if (use_rtps) {
+        // dot_product(xb',xb') in working precision, sequential like the oracle
+        T d = 0;
+#pragma unroll
+        for (int m = 0; m < 32; ++m) {
+          const T x = __shfl_sync(FULLM, xp, m);
+          d += x * x;
+        }
+        const float xb_std = (float)d;
+        const float xa_std = seq_sum32(LK_MUL(xap, xap));
+        const float fac = LK_ADD(LK_SUB(LK_MUL(rtps_alpha, LK_SQRT(LK_DIV(xb_std, xa_std))), rtps_alpha), 1.0f);
+        xap = LK_MUL(xap, fac);
+      }
+      xa32 = LK_ADD(xa_mean, xap);                                        // core:697
+    }
+    v[(int64_t)lane * npts_total + pt] = xa32;                            // core:229
+  }
+}
+
+template <typename T>
+void launch_transform32(cudaStream_t s, int64_t nunits, const int32_t *unit_pt, int64_t npts_total, int64_t pt_base,
+                        const T *U, const T *lam, const T *wbar, const int32_t *nanflag, int nfields, float *var,
+                        int use_rtpp, float rtpp_alpha, int use_rtps, float rtps_alpha, double *xa_raw) {
+  if (nunits == 0 || nfields == 0) return;
+  transform32_kernel<T><<<(unsigned)((nunits + 3) / 4), 128, 0, s>>>(nunits, unit_pt, npts_total, pt_base, U, lam,
+                                                                      wbar, nanflag, nfields, var, use_rtpp,
+                                                                      rtpp_alpha, use_rtps, rtps_alpha, xa_raw);
+  launch_counter()++;
+  LK_CUDA(cudaGetLastError());
+}
+template void launch_transform32<double>(cudaStream_t, int64_t, const int32_t *, int64_t, int64_t, const double *,
+                                         const double *, const double *, const int32_t *, int, float *, int, float,
+                                         int, float, double *);
+template void launch_transform32<float>(cudaStream_t, int64_t, const int32_t *, int64_t, int64_t, const float *,
+                                        const float *, const float *, const int32_t *, int, float *, int, float, int,
+                                        float, double *);
+
+// weights dump for the row-major U of the k = 32 path: Wa = sqrt(31) U Lambda^(-1/2) U^T
+template <typename T>
+__global__ void __launch_bounds__(256)
+    weights_dump32_kernel(int64_t nunits, const int32_t *__restrict__ unit_pt, const T *__restrict__ U,
+                          const T *__restrict__ lam, const T *__restrict__ wbar, double *__restrict__ wbar_out,
+                          double *__restrict__ Wa_out) {
+  __shared__ T sc[32];
+  const int64_t unit = blockIdx.x;
+  if (unit >= nunits) return;
+  const int64_t pt = unit_pt[unit];
+  const T *Uu = U + unit * 1024;  // U[i][l] at i*32 + l
+  if (threadIdx.x < 32) sc[threadIdx.x] = sqrt((T)31) / sqrt(lam[unit * 32 + threadIdx.x]);
+  __syncthreads();
+  if (wbar_out && threadIdx.x < 32) wbar_out[pt * 32 + threadIdx.x] = (double)wbar[unit * 32 + threadIdx.x];
+  if (Wa_out)
+    for (int e = threadIdx.x; e < 1024; e += blockDim.x) {
+      const int i = e & 31, j = e >> 5;
+      T a = 0;
+      for (int l = 0; l < 32; ++l) a += Uu[i * 32 + l] * sc[l] * Uu[j * 32 + l];
+      Wa_out[pt * 1024 + e] = (double)a;
+    }
+}
+template <typename T>
+void launch_weights_dump32(cudaStream_t s, int64_t nunits, const int32_t *unit_pt, const T *U, const T *lam,
+                           const T *wbar, double *wbar_out, double *Wa_out) {
+  if (nunits == 0) return;
+  weights_dump32_kernel<T><<<(unsigned)nunits, 256, 0, s>>>(nunits, unit_pt, U, lam, wbar, wbar_out, Wa_out);
+  launch_counter()++;
+  LK_CUDA(cudaGetLastError());
+}
+template void launch_weights_dump32<double>(cudaStream_t, int64_t, const int32_t *, const double *, const double *,
+                                            const double *, double *, double *);
+template void launch_weights_dump32<float>(cudaStream_t, int64_t, const int32_t *, const float *, const float *,
+                                           const float *, double *, double *);
+
+}  // namespace lk

@@ -168,6 +168,21 @@ void launch_yoyb_rows(cudaStream_t s, const TreeViews &tv, int k, int64_t nq, co
                       float *yo, float *yb);
 double run_fma_peak(cudaStream_t s, int kind);
 
+// ---- k = 32 fast paths (warp per analysis unit; U stored by rows: U[i][j] at i*32+j) ----------
+void launch_gram32(cudaStream_t s, const TreeViews &tv, int64_t nunits, const int32_t *unit_pt, double mu,
+                   double *C, double *b, int32_t *nanflag);
+template <typename T>
+void launch_eig32_solve(cudaStream_t s, int64_t n, T *C_inout_U, const T *b, T *lam, T *wbar, int32_t *sweeps_max);
+template <typename T>
+void launch_syevd32(cudaStream_t s, int64_t n, const T *A, T *W, T *V, int32_t *sweeps_max);
+template <typename T>
+void launch_transform32(cudaStream_t s, int64_t nunits, const int32_t *unit_pt, int64_t npts_total, int64_t pt_base,
+                        const T *U, const T *lam, const T *wbar, const int32_t *nanflag, int nfields, float *var,
+                        int use_rtpp, float rtpp_alpha, int use_rtps, float rtps_alpha, double *xa_raw);
+template <typename T>
+void launch_weights_dump32(cudaStream_t s, int64_t nunits, const int32_t *unit_pt, const T *U, const T *lam,
+                           const T *wbar, double *wbar_out, double *Wa_out);
+
 int64_t &launch_counter();
 
 }  // namespace lk
