@@ -15,6 +15,8 @@
 // Double-precision sqrt / divide in the rotation are replaced by MUFU seeds + Newton steps
 // (2 iterations: full double accuracy); exact orthogonality only needs c^2 + s^2 = 1, which
 // c = rsqrt(1 + t^2), s = c t delivers.
+#include <cstdlib>
+
 #include "letkf_internal.cuh"
 
 namespace lk {
@@ -22,12 +24,23 @@ namespace lk {
 constexpr int K32 = 32;
 constexpr unsigned FULL = 0xffffffffu;
 
+__device__ __forceinline__ float rsqrt_approx(float x) {
+  float r;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
 template <typename T>
 struct Fast;
 template <>
 struct Fast<double> {
   static __device__ __forceinline__ double rsqrt(double x) {  // x > 0 within float range
-    double r = (double)rsqrtf((float)x);
+    double r = (double)rsqrt_approx((float)x);
     const double h = 0.5 * x;
     double e = fma(-h * r, r, 0.5);
     r = fma(r, e, r);
@@ -45,17 +58,33 @@ struct Fast<double> {
     r = fma(r, e, r);
     return r;
   }
+  // one Newton step (relative error ~1e-13): enough for the rotation ANGLE, which only has to
+  // annihilate gamma approximately; c and s themselves use the full-accuracy rsqrt
+  static __device__ __forceinline__ double rsqrt1(double x) {
+    double r = (double)rsqrt_approx((float)x);
+    const double e = fma(-0.5 * x * r, r, 0.5);
+    return fma(r, e, r);
+  }
+  static __device__ __forceinline__ double rcp1(double x) {
+    float rf;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rf) : "f"((float)x));
+    double r = (double)rf;
+    const double e = fma(-x, r, 1.0);
+    return fma(r, fma(e, e, e), r);  // r (1 + e + e^2): one cubic step
+  }
   static __device__ __forceinline__ double tol2(int k) { return 4.930380657631324e-32 * k; }  // (eps sqrt k)^2
 };
 template <>
 struct Fast<float> {
   static __device__ __forceinline__ float rsqrt(float x) {
-    float r = rsqrtf(x);
+    float r = rsqrt_approx(x);
     const float h = 0.5f * x;
     const float e = fmaf(-h * r, r, 0.5f);
     return fmaf(r, e, r);
   }
   static __device__ __forceinline__ float rcp(float x) { return __frcp_rn(x); }
+  static __device__ __forceinline__ float rsqrt1(float x) { return rsqrt_approx(x); }
+  static __device__ __forceinline__ float rcp1(float x) { return __frcp_rn(x); }
   static __device__ __forceinline__ float tol2(int k) { return 1.4210855e-14f * k; }
 };
 
@@ -110,14 +139,24 @@ __device__ __forceinline__ bool warp_cholesky32(T (&g)[K32], int lane, T *colbuf
   return ok;
 }
 
-// one-sided Jacobi on the columns held as registers; returns the sweep count
-template <typename T>
-__device__ __forceinline__ int warp_jacobi32(T (&g)[K32], int lane, T *csbuf /* 32 T: (c,s) x 16 */) {
+// one-sided Jacobi on the columns held as registers; returns the sweep count.
+// csbuf: 32 T ((c,s) x 16 pairs); part: 16*32 T of shared memory private to the warp for the
+// gamma reduction.  stop2: once a whole sweep has seen only cos^2 <= stop2, quadratic convergence
+// puts every cosine after that sweep below ~stop2 (measured: 1e-6 -> 4e-13, 2.5e-9 -> 2e-16), so
+// the sweep that would merely verify convergence is skipped.
+// FASTROT: the rotation ANGLE t is evaluated in real32 (MUFU rsqrt/rcp, ~8 short-latency ops instead
+// of ~15 dependent FP64 ops); c = rsqrt(1 + t^2), s = c t stay in working precision, so every
+// rotation is orthogonal to working accuracy and only the annihilation of gamma is approximate
+// (residual cosine ~1e-7 x the old one, far inside the quadratic-convergence budget).  Needs squared
+// column norms within real32 range, which holds for LETKF matrices (eigenvalues >= (k-1)/rho).
+template <typename T, bool FASTROT>
+__device__ __forceinline__ int warp_jacobi32(T (&g)[K32], int lane, T *csbuf, T *part, T stop2) {
   const T tol2 = Fast<T>::tol2(K32);
   // lane that holds, before a rotation step, the norm this lane's register slot receives
   const int p = (lane & 1) ? 31 - (lane >> 1) : (lane >> 1);
   const int pp = p == 0 ? 0 : (p == 1 ? 31 : p - 1);
   const int src_lane = pp <= 15 ? 2 * pp : 2 * (31 - pp) + 1;
+  const T *mypart = part + (lane >> 1) * 32 + (lane & 1) * 16;
   int sweeps = 0;
   for (; sweeps < 30; ++sweeps) {
     // exact squared column norms: lane l <- ||column in register slot l||^2
@@ -129,26 +168,45 @@ __device__ __forceinline__ int warp_jacobi32(T (&g)[K32], int lane, T *csbuf /* 
       transposed_reduce<T, K32>(sq, lane);
       d = sq[0];
     }
-    int rotated = 0;
+    int rotated = 0, big = 0;
 #pragma unroll 1
     for (int step = 0; step < K32 - 1; ++step) {
-      T gam[16];
+      // gamma_n = sum over lanes of g[2n] g[2n+1]: partial products through shared memory; lane
+      // 2n+h adds the 16 partials of lanes 16h..16h+15, then one exchange with its partner.  The
+      // read index is skewed by the lane so that every bank serves exactly two lanes.
 #pragma unroll
-      for (int n = 0; n < 16; ++n) gam[n] = g[2 * n] * g[2 * n + 1];
-      transposed_reduce<T, 16>(gam, lane);
-      const T gamma = gam[0];
+      for (int n = 0; n < 16; ++n) part[n * 32 + lane] = g[2 * n] * g[2 * n + 1];
+      __syncwarp();
+      T gamma;
+      {
+        T acc[4] = {T(0), T(0), T(0), T(0)};
+#pragma unroll
+        for (int r = 0; r < 16; ++r) acc[r & 3] += mypart[(r + lane) & 15];
+        gamma = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+        gamma += __shfl_xor_sync(FULL, gamma, 1);
+      }
       const T dpart = __shfl_xor_sync(FULL, d, 1);
       const T alpha = (lane & 1) ? dpart : d;
       const T beta = (lane & 1) ? d : dpart;
-      const bool rot = gamma * gamma > tol2 * alpha * beta;
+      const T g2 = gamma * gamma, ab = alpha * beta;
+      const bool rot = g2 > tol2 * ab;
+      big |= g2 > stop2 * ab;
       T c = T(1), s = T(0), t = T(0);
       {
         const T delta = beta - alpha;
-        T x = fma(delta, delta, T(4) * gamma * gamma);
-        x = rot ? x : T(1);
-        const T h = x * Fast<T>::rsqrt(x);
-        const T den = fabs(delta) + h;
-        const T tt = (delta >= T(0) ? T(2) : T(-2)) * gamma * Fast<T>::rcp(den);
+        T tt;
+        if (FASTROT) {
+          const float df = (float)delta, gf = (float)gamma;
+          const float x = fmaxf(fmaf(df, df, 4.f * gf * gf), 1e-30f);
+          const float h = x * rsqrt_approx(x);
+          tt = (T)((df >= 0.f ? 2.f : -2.f) * gf * rcp_approx(fabsf(df) + h));
+        } else {
+          T x = fma(delta, delta, T(4) * g2);
+          x = rot ? x : T(1);
+          const T h = x * Fast<T>::rsqrt1(x);
+          const T den = fabs(delta) + h;
+          tt = (delta >= T(0) ? T(2) : T(-2)) * gamma * Fast<T>::rcp1(den);
+        }
         const T cc = Fast<T>::rsqrt(fma(tt, tt, T(1)));
         if (rot) {
           t = tt;
@@ -158,7 +216,6 @@ __device__ __forceinline__ int warp_jacobi32(T (&g)[K32], int lane, T *csbuf /* 
       }
       rotated |= rot;
       d = (lane & 1) ? fma(t, gamma, d) : fma(-t, gamma, d);  // beta + t gamma | alpha - t gamma
-      __syncwarp();
       if (!(lane & 1)) {
         csbuf[lane] = c;      // pair n = lane/2 -> csbuf[2n], csbuf[2n+1]
         csbuf[lane + 1] = s;
@@ -180,8 +237,9 @@ __device__ __forceinline__ int warp_jacobi32(T (&g)[K32], int lane, T *csbuf /* 
         for (int m = 0; m < K32; ++m) g[m] = ng[m];
       }
       d = __shfl_sync(FULL, d, src_lane);
+      __syncwarp();  // csbuf / part are rewritten by the next step
     }
-    if (!__any_sync(FULL, rotated)) {
+    if (!__any_sync(FULL, rotated) || !__any_sync(FULL, big)) {
       ++sweeps;
       break;
     }
@@ -191,12 +249,12 @@ __device__ __forceinline__ int warp_jacobi32(T (&g)[K32], int lane, T *csbuf /* 
 
 // MODE 0: C (row-major lower / symmetric full, SPD), b -> U^T-by-rows (U[i][j] at i*32+j), lam, wbar
 // MODE 1: A (column-major, lower referenced) -> W ascending, V column-major
-template <typename T, int MODE>
-__global__ void __launch_bounds__(128)
+template <typename T, int MODE, int MINB>
+__global__ void __launch_bounds__(128, MINB)
     eig32_warp_kernel(int64_t n, T *__restrict__ Cio, const T *__restrict__ bvec, T *__restrict__ lam,
                       T *__restrict__ wbar, const T *__restrict__ Ain, T *__restrict__ Wout,
                       T *__restrict__ Vout, int32_t *__restrict__ sweeps_max) {
-  __shared__ __align__(16) T sbuf[4][64];
+  __shared__ __align__(16) T sbuf[4][64 + 16 * 32];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int64_t u = (int64_t)blockIdx.x * 4 + w;
   if (u >= n) return;
@@ -252,7 +310,10 @@ __global__ void __launch_bounds__(128)
     }
   }
 
-  const int sweeps = warp_jacobi32<T>(g, lane, buf);
+  // MODE 0 feeds the LETKF weights (1e-10 bar): stop once a sweep saw only |cos| <= 1e-7.
+  // MODE 1 is the general eigensolver: |cos| <= 1e-9 before the last sweep.
+  const T stop2 = MODE == 0 ? T(1e-14) : (sizeof(T) == 8 ? T(1e-18) : T(1e-9));
+  const int sweeps = warp_jacobi32<T, MODE == 0>(g, lane, buf, buf + 64, stop2);
   if (lane == 0 && sweeps_max) atomicMax(sweeps_max, sweeps);
 
   // eigenvalues = squared column norms (lane j <- lambda_j), eigenvectors = normalised columns
@@ -314,16 +375,24 @@ template <typename T>
 void launch_eig32_solve(cudaStream_t s, int64_t n, T *C_inout_U, const T *b, T *lam, T *wbar,
                         int32_t *sweeps_max) {
   if (n == 0) return;
-  eig32_warp_kernel<T, 0><<<(unsigned)((n + 3) / 4), 128, 0, s>>>(n, C_inout_U, b, lam, wbar, nullptr, nullptr,
-                                                                   nullptr, sweeps_max);
+  static const int occ = [] {
+    const char *e = getenv("LETKF_B200_EIG_OCC");
+    return e ? atoi(e) : 4;
+  }();
+  if (occ == 4)
+    eig32_warp_kernel<T, 0, 4><<<(unsigned)((n + 3) / 4), 128, 0, s>>>(n, C_inout_U, b, lam, wbar, nullptr, nullptr,
+                                                                        nullptr, sweeps_max);
+  else
+    eig32_warp_kernel<T, 0, 3><<<(unsigned)((n + 3) / 4), 128, 0, s>>>(n, C_inout_U, b, lam, wbar, nullptr, nullptr,
+                                                                        nullptr, sweeps_max);
   launch_counter()++;
   LK_CUDA(cudaGetLastError());
 }
 template <typename T>
 void launch_syevd32(cudaStream_t s, int64_t n, const T *A, T *W, T *V, int32_t *sweeps_max) {
   if (n == 0) return;
-  eig32_warp_kernel<T, 1><<<(unsigned)((n + 3) / 4), 128, 0, s>>>(n, nullptr, nullptr, nullptr, nullptr, A, W, V,
-                                                                   sweeps_max);
+  eig32_warp_kernel<T, 1, 2><<<(unsigned)((n + 3) / 4), 128, 0, s>>>(n, nullptr, nullptr, nullptr, nullptr, A, W, V,
+                                                                      sweeps_max);
   launch_counter()++;
   LK_CUDA(cudaGetLastError());
 }
