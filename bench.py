@@ -186,6 +186,7 @@ def main():
     import torch
     import torch.distributed as dist
     from cwbnwp_letkf_b200 import host as H
+    from cwbnwp_letkf_b200 import partition as P
 
     torch.cuda.set_device(local_rank)
     if world > 1:
@@ -204,16 +205,13 @@ def main():
             eng.set_obs(o)
             continue
         n, nv = o.n, o.nvar
-        lo, hi = rank * k // world, (rank + 1) * k // world
-        assert k % world == 0
+        lo, hi = P.member_slice(rank, world, k)
         mine = torch.from_numpy(np.ascontiguousarray(o.hdxb[lo:hi])).to(dev)      # this rank "read" members lo:hi
-        full = torch.empty((k, n, nv), dtype=torch.float32, device=dev)
-        dist.all_gather_into_tensor(full, mine)
+        full = P.allgather_members(mine, k, rank, world)
         qc = None
         if o.qc is not None:
             mq = torch.from_numpy(np.ascontiguousarray(o.qc[lo:hi])).to(dev)
-            qc = torch.empty((k, n, nv), dtype=torch.int32, device=dev)
-            dist.all_gather_into_tensor(qc, mq)
+            qc = P.allgather_members(mq, k, rank, world)
         xyz = torch.from_numpy(o.xyz).to(dev)
         obs = torch.from_numpy(o.obs).to(dev)
         err = None if o.error is None else torch.from_numpy(o.error).to(dev)
@@ -223,10 +221,8 @@ def main():
     torch.cuda.synchronize()
     t_obs = time.perf_counter() - t_obs0
 
-    # ---- this rank's columns (cyclic, module_mpi_util.f90:80-127) ----
-    ncol = sc.nx * sc.ny
-    cols = np.arange(rank, ncol, world)
-    pts = (cols[None, :] + ncol * np.arange(sc.nz)[:, None]).reshape(-1)
+    # ---- this rank's columns (2-D cyclic process grid, module_mpi_util.f90:80-127) ----
+    pts = P.local_points(rank, world, sc.nx, sc.ny, sc.nz)
     xyz_local = np.ascontiguousarray(sc.xyz_grid[pts]) if world > 1 else sc.xyz_grid
     npts_local = xyz_local.shape[0]
     total_pts = sc.npts
