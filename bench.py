@@ -373,4 +373,25 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    # The contract is ONE JSON line on stdout.  Native libraries (NCCL prints its version banner) write
+    # to fd 1 behind Python's back, so fd 1 is pointed at stderr while the benchmark runs and restored
+    # for the final line.
+    sys.stdout.flush()
+    _saved = os.dup(1)
+    os.dup2(2, 1)
+    import io
+    _buf = io.StringIO()
+    _py_stdout = sys.stdout
+    sys.stdout = _buf
+    try:
+        main()
+    finally:
+        sys.stdout = _py_stdout
+        sys.stdout.flush()
+        os.dup2(_saved, 1)
+        os.close(_saved)
+    lines = [l for l in _buf.getvalue().splitlines() if l.strip()]
+    for l in lines[:-1]:
+        print(l, file=sys.stderr)
+    if lines:
+        print(lines[-1], flush=True)
