@@ -1,128 +1,238 @@
-// Batched symmetric eigensolver -- the ?syevd('V','L') of module_eigen.f90:49/66, one matrix per
-// analysis unit -- and the Pa~ b product that follows it (module_letkf_core.f90:651-652).
+// Batched symmetric eigensolver, any k <= 256 -- the ?syevd('V','L') of module_eigen.f90:49/66, one
+// matrix per analysis unit -- and the Pa~ b product that follows it (module_letkf_core.f90:651-652).
 //
-// Method: for a symmetric positive definite C (the LETKF matrix (k-1)/rho I + Yb Yb^T always is),
-// factor C = L L^T (Cholesky) and orthogonalise the COLUMNS of L by one-sided (Hestenes) Jacobi
-// rotations, L J1 J2 ... = U Sigma.  Then C = U Sigma^2 U^T: eigenvalues are the squared column
-// norms, eigenvectors the normalised columns -- no separate eigenvector accumulation, and the
-// Cholesky factor preconditions the iteration (Veselic-Hari), so 5-7 sweeps reach working
-// precision.  General symmetric input (the stand-alone eigensolver entry point) is shifted by a
-// Gershgorin bound to make it definite and the shift is removed from the eigenvalues.
+// Method (same as the k = 32 warp kernel): for SPD C factor C = L L^T and orthogonalise the COLUMNS of
+// L by one-sided Jacobi rotations, L J1 J2 ... = U Sigma, so C = U Sigma^2 U^T: eigenvalues are squared
+// column norms, eigenvectors the normalised columns; no eigenvector accumulation, and the Cholesky
+// factor preconditions the iteration.  General symmetric input (stand-alone entry point) is first
+// tried unshifted and otherwise shifted by a Gershgorin bound.
 //
-// This file holds the generic block-per-matrix kernel (any k <= 256, either precision): the
-// factor lives in shared memory when k*k*sizeof(T) fits, otherwise in place in global memory
-// (L2-resident).  Column pairs of a round-robin ordering are processed one pair per warp with
-// shuffle reductions for the three inner products.
-#include "letkf_internal.cuh"
+// One CTA per matrix; the factor lives in shared memory (k <= 160 FP64 / 224 FP32) or in place in
+// global memory (L2) for larger k.  A plain shared-memory Jacobi is bandwidth bound: each rotation
+// moves 32 B per row pair for 5 FMAs, 3x more than the 128 B/clk/SM the SM delivers per FP64 FMA.
+// So the sweep is REGISTER BLOCKED: columns are grouped in blocks of 4; a warp loads two blocks
+// (8 columns, rows split over the lanes) into registers, performs the 16 cross rotations as 4 rounds
+// of 4 disjoint pairs, and stores them back -- 4x less shared-memory traffic per rotation.  Block
+// pairs follow a round-robin schedule (nb-1 outer steps of nb/2 disjoint block pairs, one per warp);
+// the 6 pairs inside each block are rotated once per sweep in a separate pass that also refreshes
+// the exact column norms.  Within a round the 4 inner products are summed with one transposed
+// butterfly so that every 8-lane group ends up with one gamma and computes one rotation; squared
+// norms are carried in shared memory with the rotation update formulas.
+#include "eig_common.cuh"
 
 namespace lk {
 
-template <typename T>
-struct Eps;
-template <>
-struct Eps<double> {
-  static __device__ __forceinline__ double tol(int k) { return 2.220446049250313e-16 * sqrt((double)k); }
-  static __device__ __forceinline__ double tiny() { return 1e-290; }
-};
-template <>
-struct Eps<float> {
-  static __device__ __forceinline__ float tol(int k) { return 1.1920929e-7f * sqrtf((float)k); }
-  static __device__ __forceinline__ float tiny() { return 1e-30f; }
-};
+constexpr unsigned FULLW = 0xffffffffu;
 
 template <typename T>
 __device__ __forceinline__ T warp_sum(T v) {
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULLW, v, o);
   return v;
 }
 
-// Cholesky in place on the lower triangle of G (column-major, ld = k), then zero the strict
-// upper triangle.  Whole CTA participates.
+// 4 per-lane partial sums -> lane l holds the warp total of element l>>3
 template <typename T>
-__device__ bool block_cholesky(T *G, int k) {
+__device__ __forceinline__ T reduce4(T v0, T v1, T v2, T v3, int lane) {
+  const bool u16 = lane & 16, u8 = lane & 8;
+  const T w0 = (u16 ? v2 : v0) + __shfl_xor_sync(FULLW, u16 ? v0 : v2, 16);
+  const T w1 = (u16 ? v3 : v1) + __shfl_xor_sync(FULLW, u16 ? v1 : v3, 16);
+  T z = (u8 ? w1 : w0) + __shfl_xor_sync(FULLW, u8 ? w0 : w1, 8);
+  z += __shfl_xor_sync(FULLW, z, 4);
+  z += __shfl_xor_sync(FULLW, z, 2);
+  z += __shfl_xor_sync(FULLW, z, 1);
+  return z;
+}
+// 2 per-lane partial sums -> lane l holds the warp total of element l>>4
+template <typename T>
+__device__ __forceinline__ T reduce2(T v0, T v1, int lane) {
+  const bool u16 = lane & 16;
+  T z = (u16 ? v1 : v0) + __shfl_xor_sync(FULLW, u16 ? v0 : v1, 16);
+  z += __shfl_xor_sync(FULLW, z, 8);
+  z += __shfl_xor_sync(FULLW, z, 4);
+  z += __shfl_xor_sync(FULLW, z, 2);
+  z += __shfl_xor_sync(FULLW, z, 1);
+  return z;
+}
+
+// Cholesky in place on the lower triangle of G (column-major, leading dimension ld), then zero the
+// strict upper triangle.  Whole CTA participates.  Returns false if a pivot is not positive.
+template <typename T>
+__device__ bool block_cholesky(T *G, int k, int ld) {
   const int tid = threadIdx.x, nt = blockDim.x;
   const int warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
   bool ok = true;  // every thread reads the same pivots, so this is CTA-uniform
   for (int j = 0; j < k; ++j) {
     __syncthreads();
-    const T piv = G[j + (size_t)j * k];
+    const T piv = G[j + (size_t)j * ld];
     if (!(piv > T(0))) ok = false;
     const T d = sqrt(piv);
     __syncthreads();
-    if (tid == 0) G[j + (size_t)j * k] = d;
+    if (tid == 0) G[j + (size_t)j * ld] = d;
     const T dinv = T(1) / d;
-    for (int i = j + 1 + tid; i < k; i += nt) G[i + (size_t)j * k] *= dinv;
+    for (int i = j + 1 + tid; i < k; i += nt) G[i + (size_t)j * ld] *= dinv;
     __syncthreads();
     for (int c = j + 1 + warp; c < k; c += nw) {
-      const T f = G[c + (size_t)j * k];
-      for (int i = c + lane; i < k; i += 32) G[i + (size_t)c * k] -= G[i + (size_t)j * k] * f;
+      const T f = G[c + (size_t)j * ld];
+      for (int i = c + lane; i < k; i += 32) G[i + (size_t)c * ld] -= G[i + (size_t)j * ld] * f;
     }
   }
   __syncthreads();
   for (int e = tid; e < k * k; e += nt) {
     const int i = e % k, j = e / k;
-    if (i < j) G[e] = T(0);
+    if (i < j) G[i + (size_t)j * ld] = T(0);
   }
   __syncthreads();
   return ok;
 }
 
-// One-sided Jacobi sweeps on the columns of G until every pair is orthogonal to tolerance.
-// Returns the number of sweeps.  Round-robin (tournament) ordering on kk = k rounded up to even.
-template <typename T>
-__device__ int block_jacobi(T *G, int k) {
-  const int tid = threadIdx.x, nt = blockDim.x;
-  const int warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
-  const int kk = (k + 1) & ~1;
-  const int half = kk / 2, nm1 = kk - 1;
-  const T tol = Eps<T>::tol(k);
+// One rotation round inside a warp's register tile.  NP = pairs rotated simultaneously (4 for a block
+// pair, 2 inside a block); pair i rotates register columns PA[i], PB[i] (compile time) which are the
+// matrix columns colA, colB of THIS lane's pair (the pair with index lane / (32/NP)).
+template <typename T, int RPL, int NC, int NP, bool FASTROT>
+struct RoundOp {
+  template <typename PA, typename PB>
+  static __device__ __forceinline__ void run(T (&x)[NC][RPL], PA pa, PB pb, int colA, int colB, T *nrm, int lane,
+                                             T tol2, T stop2, int &rotated, int &big) {
+    constexpr int GRP = 32 / NP;
+    T part[NP];
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+      T a = T(0);
+#pragma unroll
+      for (int m = 0; m < RPL; ++m) a = fma(x[pa(i)][m], x[pb(i)][m], a);
+      part[i] = a;
+    }
+    T gamma;
+    if (NP == 4)
+      gamma = reduce4(part[0], part[1], part[NP > 2 ? 2 : 0], part[NP > 2 ? 3 : 0], lane);
+    else
+      gamma = reduce2(part[0], part[1], lane);
+    const T alpha = nrm[colA], beta = nrm[colB];
+    const T g2 = gamma * gamma, ab = alpha * beta;
+    const bool rot = g2 > tol2 * ab;
+    big |= g2 > stop2 * ab;
+    rotated |= rot;
+    T c, s, t;
+    jacobi_rotation<T, FASTROT>(alpha, beta, gamma, rot, c, s, t);
+    __syncwarp();
+    if ((lane & (GRP - 1)) == 0) {
+      nrm[colA] = fma(-t, gamma, alpha);
+      nrm[colB] = fma(t, gamma, beta);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+      const T ci = __shfl_sync(FULLW, c, i * GRP), si = __shfl_sync(FULLW, s, i * GRP);
+#pragma unroll
+      for (int m = 0; m < RPL; ++m) {
+        const T a = x[pa(i)][m], b = x[pb(i)][m];
+        x[pa(i)][m] = fma(ci, a, -(si * b));
+        x[pb(i)][m] = fma(si, a, ci * b);
+      }
+    }
+  }
+};
+
+// One-sided Jacobi sweeps, register blocked.  G: kp columns (kp multiple of 8, columns >= k are zero)
+// of ld rows (rows >= k are zero / absent; lanes only touch rows < nrows).  nrm: kp values of shared
+// memory.  Returns the number of sweeps.
+template <typename T, int RPL, bool FASTROT>
+__device__ int block_jacobi_rb(T *G, int k, int kp, int ld, int nrows, T *nrm, T stop2) {
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31, nw = blockDim.x >> 5;
+  const int nb = kp / 4, npair = nb / 2, nm1 = nb - 1;
+  const T tol2 = Fast<T>::tol2(k);
+  bool rowok[RPL];
+#pragma unroll
+  for (int m = 0; m < RPL; ++m) rowok[m] = lane + 32 * m < nrows;
   int sweeps = 0;
-  for (; sweeps < 60; ++sweeps) {
-    int rotated = 0;
-    for (int step = 0; step < nm1; ++step) {
-      for (int pi = warp; pi < half; pi += nw) {
-        int p, q;
-        if (pi == 0) {
-          p = nm1;
-          q = step;
+  for (; sweeps < 40; ++sweeps) {
+    int rotated = 0, big = 0;
+    // ---- pass 1: pairs inside each block of 4 columns, plus exact column norms ------------------
+    for (int I = warp; I < nb; I += nw) {
+      T x[4][RPL];
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int m = 0; m < RPL; ++m) x[c][m] = rowok[m] ? G[(size_t)(4 * I + c) * ld + lane + 32 * m] : T(0);
+      {
+        T sq[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          T a = T(0);
+#pragma unroll
+          for (int m = 0; m < RPL; ++m) a = fma(x[c][m], x[c][m], a);
+          sq[c] = a;
+        }
+        const T nn = reduce4(sq[0], sq[1], sq[2], sq[3], lane);
+        if ((lane & 7) == 0) nrm[4 * I + (lane >> 3)] = nn;
+        __syncwarp();
+      }
+      const int h = lane >> 4;  // which of the 2 simultaneous pairs this lane works for
+      // round 0: (0,1) (2,3)   round 1: (0,2) (1,3)   round 2: (0,3) (1,2)
+      RoundOp<T, RPL, 4, 2, FASTROT>::run(
+          x, [](int i) { return 2 * i; }, [](int i) { return 2 * i + 1; }, 4 * I + 2 * h, 4 * I + 2 * h + 1, nrm, lane,
+          tol2, stop2, rotated, big);
+      RoundOp<T, RPL, 4, 2, FASTROT>::run(
+          x, [](int i) { return i; }, [](int i) { return i + 2; }, 4 * I + h, 4 * I + h + 2, nrm, lane, tol2, stop2,
+          rotated, big);
+      RoundOp<T, RPL, 4, 2, FASTROT>::run(
+          x, [](int i) { return i; }, [](int i) { return 3 - i; }, 4 * I + h, 4 * I + 3 - h, nrm, lane, tol2, stop2,
+          rotated, big);
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int m = 0; m < RPL; ++m)
+          if (rowok[m]) G[(size_t)(4 * I + c) * ld + lane + 32 * m] = x[c][m];
+    }
+    __syncthreads();
+    // ---- pass 2: all cross pairs of every block pair, round-robin over the blocks ----------------
+    for (int os = 0; os < nm1; ++os) {
+      for (int j = warp; j < npair; j += nw) {
+        int I, J;
+        if (j == 0) {
+          I = nm1;
+          J = os;
         } else {
-          p = (step + pi) % nm1;
-          q = (step - pi + nm1) % nm1;
+          I = (os + j) % nm1;
+          J = (os - j + nm1) % nm1;
         }
-        if (p > q) {
-          const int t = p;
-          p = q;
-          q = t;
-        }
-        if (q >= k) continue;  // dummy column of the odd-k padding
-        T *gp = G + (size_t)p * k, *gq = G + (size_t)q * k;
-        T a = 0, b = 0, g = 0;
-        for (int i = lane; i < k; i += 32) {
-          const T x = gp[i], y = gq[i];
-          a += x * x;
-          b += y * y;
-          g += x * y;
-        }
-        a = warp_sum(a);
-        b = warp_sum(b);
-        g = warp_sum(g);
-        if (fabs(g) > tol * sqrt(a * b) && fabs(g) > Eps<T>::tiny()) {
-          const T zeta = (b - a) / (T(2) * g);
-          const T t = (zeta >= 0 ? T(1) : T(-1)) / (fabs(zeta) + sqrt(T(1) + zeta * zeta));
-          const T c = T(1) / sqrt(T(1) + t * t);
-          const T s = c * t;
-          for (int i = lane; i < k; i += 32) {
-            const T x = gp[i], y = gq[i];
-            gp[i] = c * x - s * y;
-            gq[i] = s * x + c * y;
+        T x[8][RPL];
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+          for (int m = 0; m < RPL; ++m) {
+            x[c][m] = rowok[m] ? G[(size_t)(4 * I + c) * ld + lane + 32 * m] : T(0);
+            x[4 + c][m] = rowok[m] ? G[(size_t)(4 * J + c) * ld + lane + 32 * m] : T(0);
           }
-          rotated = 1;
-        }
+        const int i = lane >> 3;  // this lane's pair within a round
+        RoundOp<T, RPL, 8, 4, FASTROT>::run(
+            x, [](int i) { return i; }, [](int i) { return 4 + i; }, 4 * I + i, 4 * J + i, nrm, lane, tol2, stop2, rotated,
+            big);
+        RoundOp<T, RPL, 8, 4, FASTROT>::run(
+            x, [](int i) { return i; }, [](int i) { return 4 + ((i + 1) & 3); }, 4 * I + i, 4 * J + ((i + 1) & 3), nrm,
+            lane, tol2, stop2, rotated, big);
+        RoundOp<T, RPL, 8, 4, FASTROT>::run(
+            x, [](int i) { return i; }, [](int i) { return 4 + ((i + 2) & 3); }, 4 * I + i, 4 * J + ((i + 2) & 3), nrm,
+            lane, tol2, stop2, rotated, big);
+        RoundOp<T, RPL, 8, 4, FASTROT>::run(
+            x, [](int i) { return i; }, [](int i) { return 4 + ((i + 3) & 3); }, 4 * I + i, 4 * J + ((i + 3) & 3), nrm,
+            lane, tol2, stop2, rotated, big);
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+          for (int m = 0; m < RPL; ++m)
+            if (rowok[m]) {
+              G[(size_t)(4 * I + c) * ld + lane + 32 * m] = x[c][m];
+              G[(size_t)(4 * J + c) * ld + lane + 32 * m] = x[4 + c][m];
+            }
       }
       __syncthreads();
     }
-    if (!__syncthreads_or(rotated)) {
+    const int any_rot = __syncthreads_or(rotated);
+    const int any_big = __syncthreads_or(big);
+    if (!any_rot || !any_big) {
       ++sweeps;
       break;
     }
@@ -130,42 +240,49 @@ __device__ int block_jacobi(T *G, int k) {
   return sweeps;
 }
 
-// mode 0: LETKF solve.  in: C (full symmetric, SPD), b.  out: U (in place of C), lam, wbar.
+// mode 0: LETKF solve.  in: C (full symmetric, SPD), b.  out: U (column-major, in place of C), lam, wbar.
 // mode 1: ?syevd.      in: A (lower).                  out: W ascending, V.
-template <typename T, int MODE, bool SMEM>
-__global__ void __launch_bounds__(256)
-    eig_block_kernel(int k, int64_t n, T *__restrict__ Cio, const T *__restrict__ bvec, T *__restrict__ lam,
-                     T *__restrict__ wbar, const T *__restrict__ Ain, T *__restrict__ Wout,
-                     T *__restrict__ Vout, int32_t *__restrict__ sweeps_max) {
+template <typename T, int MODE, int RPL, bool SMEM>
+__global__ void __launch_bounds__(RPL >= 5 ? 256 : 512)
+    eig_blk_kernel(int k, int64_t n, T *__restrict__ Cio, const T *__restrict__ bvec, T *__restrict__ lam,
+                   T *__restrict__ wbar, const T *__restrict__ Ain, T *__restrict__ Wout, T *__restrict__ Vout,
+                   int32_t *__restrict__ sweeps_max) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T *sm = reinterpret_cast<T *>(smem_raw);
   const int64_t u = blockIdx.x;
   if (u >= n) return;
   const int tid = threadIdx.x, nt = blockDim.x;
   const int warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
-  T *vec1 = sm;        // [k]
-  T *vec2 = sm + k;    // [k]
-  T *Gs = sm + 2 * k;  // [k*k] when SMEM
+  const int kp = (k + 7) & ~7;
+  const int ld = SMEM ? 32 * RPL : k;  // in-place global storage requires k % 32 == 0 (checked on the host)
+  T *vec1 = sm;             // [kp]
+  T *vec2 = sm + kp;        // [kp]
+  T *nrm = sm + 2 * kp;     // [kp]
+  T *Gs = sm + 3 * kp;      // [kp * ld] when SMEM
   T *Gg = MODE == 0 ? Cio + u * (int64_t)k * k : Vout + u * (int64_t)k * k;
   T *G = SMEM ? Gs : Gg;
   __shared__ T s_shift;
+  __shared__ T red_lo[512], red_sc[512];
 
+  if (SMEM) {
+    for (int e = tid; e < kp * ld; e += nt) G[e] = T(0);
+    __syncthreads();
+  }
   if (MODE == 0) {
     if (SMEM)
-      for (int e = tid; e < k * k; e += nt) G[e] = Gg[e];
+      for (int e = tid; e < k * k; e += nt) G[(e % k) + (size_t)(e / k) * ld] = Gg[e];
     if (tid == 0) s_shift = T(0);
     __syncthreads();
-    block_cholesky(G, k);  // C is SPD by construction; a NaN input propagates
+    block_cholesky(G, k, ld);  // C is SPD by construction; a NaN input propagates
   } else {
     const T *A = Ain + u * (int64_t)k * k;
-    __shared__ T red_lo[256], red_sc[256];
     // First try the matrix as it is (an SPD input keeps its full relative accuracy); if a pivot
     // fails, shift by a Gershgorin bound so that it becomes definite and factor again.
     for (int attempt = 0; attempt < 2; ++attempt) {
       __syncthreads();
       for (int e = tid; e < k * k; e += nt) {  // symmetrise from the lower triangle
         const int i = e % k, j = e / k;
-        G[e] = i >= j ? A[i + (size_t)j * k] : A[j + (size_t)i * k];
+        G[i + (size_t)j * ld] = i >= j ? A[i + (size_t)j * k] : A[j + (size_t)i * k];
       }
       if (tid == 0 && attempt == 0) s_shift = T(0);
       __syncthreads();
@@ -175,35 +292,39 @@ __global__ void __launch_bounds__(256)
         for (int i = tid; i < k; i += nt) {
           T off = 0;
           for (int j = 0; j < k; ++j)
-            if (j != i) off += fabs(G[i + (size_t)j * k]);
-          lowest = min(lowest, G[i + (size_t)i * k] - off);
-          scale = max(scale, fabs(G[i + (size_t)i * k]) + off);
+            if (j != i) off += fabs(G[i + (size_t)j * ld]);
+          lowest = min(lowest, G[i + (size_t)i * ld] - off);
+          scale = max(scale, fabs(G[i + (size_t)i * ld]) + off);
         }
         red_lo[tid] = lowest;
         red_sc[tid] = scale;
         __syncthreads();
-        for (int o = 128; o > 0; o >>= 1) {
-          if (tid < o) {
-            red_lo[tid] = min(red_lo[tid], red_lo[tid + o]);
-            red_sc[tid] = max(red_sc[tid], red_sc[tid + o]);
+        if (tid == 0) {
+          T lo = red_lo[0], sc = red_sc[0];
+          for (int i = 1; i < nt; ++i) {
+            lo = min(lo, red_lo[i]);
+            sc = max(sc, red_sc[i]);
           }
-          __syncthreads();
+          s_shift = sc * T(1e-3) - min(lo, T(0));
         }
-        if (tid == 0) s_shift = red_sc[0] * T(1e-3) - min(red_lo[0], T(0));
         __syncthreads();
         const T sh = s_shift;
-        for (int i = tid; i < k; i += nt) G[i + (size_t)i * k] += sh;
+        for (int i = tid; i < k; i += nt) G[i + (size_t)i * ld] += sh;
         __syncthreads();
       }
-      if (block_cholesky(G, k)) break;
+      if (block_cholesky(G, k, ld)) break;
     }
   }
-  const int sweeps = block_jacobi(G, k);
+
+  // MODE 0 feeds the LETKF weights (1e-10 bar): stop once a sweep saw only |cos| <= 1e-7 and take the
+  // rotation angle in real32.  MODE 1 is the general eigensolver: |cos| <= 1e-9, angle in working precision.
+  const T stop2 = MODE == 0 ? T(1e-14) : (sizeof(T) == 8 ? T(1e-18) : T(1e-9));
+  const int sweeps = block_jacobi_rb<T, RPL, MODE == 0>(G, k, kp, ld, k, nrm, stop2);
   if (tid == 0 && sweeps_max) atomicMax(sweeps_max, sweeps);
 
   // column norms -> eigenvalues; normalise columns -> eigenvectors
   for (int j = warp; j < k; j += nw) {
-    T *gj = G + (size_t)j * k;
+    T *gj = G + (size_t)j * ld;
     T a = 0;
     for (int i = lane; i < k; i += 32) a += gj[i] * gj[i];
     a = warp_sum(a);
@@ -217,7 +338,7 @@ __global__ void __launch_bounds__(256)
     // wbar = U diag(1/lam) U^T b   (inverse_matrix + ?gemv + ?symv, eig:37-76, core:651-652)
     const T *b = bvec + u * (int64_t)k;
     for (int j = warp; j < k; j += nw) {
-      const T *gj = G + (size_t)j * k;
+      const T *gj = G + (size_t)j * ld;
       T a = 0;
       for (int i = lane; i < k; i += 32) a += gj[i] * b[i];
       a = warp_sum(a);
@@ -226,15 +347,16 @@ __global__ void __launch_bounds__(256)
     __syncthreads();
     for (int i = tid; i < k; i += nt) {
       T a = 0;
-      for (int j = 0; j < k; ++j) a += G[i + (size_t)j * k] * vec2[j];
+      for (int j = 0; j < k; ++j) a += G[i + (size_t)j * ld] * vec2[j];
       wbar[u * (int64_t)k + i] = a;
       lam[u * (int64_t)k + i] = vec1[i];
     }
     if (SMEM)
-      for (int e = tid; e < k * k; e += nt) Gg[e] = G[e];
+      for (int e = tid; e < k * k; e += nt) Gg[e] = G[(e % k) + (size_t)(e / k) * ld];
   } else {
     // ascending order like LAPACK: rank by counting
     const T sh = s_shift;
+    int *rank = reinterpret_cast<int *>(vec2);
     for (int j = tid; j < k; j += nt) {
       const T lj = vec1[j];
       int r = 0;
@@ -242,35 +364,36 @@ __global__ void __launch_bounds__(256)
         const T ll = vec1[l];
         r += (ll < lj) || (ll == lj && l < j);
       }
-      ((int *)vec2)[j] = r;
+      rank[j] = r;
       Wout[u * (int64_t)k + r] = lj - sh;
     }
     __syncthreads();
     if (SMEM) {
       for (int e = tid; e < k * k; e += nt) {
         const int i = e % k, j = e / k;
-        Gg[i + (size_t)((int *)vec2)[j] * k] = G[e];
+        Gg[i + (size_t)rank[j] * k] = G[i + (size_t)j * ld];
       }
     } else {
-      // in-place column permutation in global memory: cycle-follow, one thread per row
+      // in-place column permutation in global memory: every thread owns rows and walks the cycles
       for (int i = tid; i < k; i += nt) {
-        // rows are independent; permute row i across columns using a register-free cycle walk
         for (int start = 0; start < k; ++start) {
-          // process each cycle once, from its smallest index
-          int c = ((int *)vec2)[start];
+          int c = rank[start];
           bool smallest = true;
           while (c != start) {
-            if (c < start) { smallest = false; break; }
-            c = ((int *)vec2)[c];
+            if (c < start) {
+              smallest = false;
+              break;
+            }
+            c = rank[c];
           }
           if (!smallest) continue;
           T carry = G[i + (size_t)start * k];
-          int dst = ((int *)vec2)[start];
+          int dst = rank[start];
           while (dst != start) {
             const T tmp = G[i + (size_t)dst * k];
             G[i + (size_t)dst * k] = carry;
             carry = tmp;
-            dst = ((int *)vec2)[dst];
+            dst = rank[dst];
           }
           G[i + (size_t)start * k] = carry;
         }
@@ -279,38 +402,55 @@ __global__ void __launch_bounds__(256)
   }
 }
 
-template <typename T>
-static size_t eig_smem_bytes(int k, bool smem_matrix) {
-  return sizeof(T) * (2 * (size_t)k + (smem_matrix ? (size_t)k * k : 0));
-}
-
-template <typename T, int MODE>
-static void launch_eig_generic(cudaStream_t s, int k, int64_t n, T *Cio, const T *b, T *lam, T *wbar,
-                               const T *A, T *W, T *V, int32_t *sweeps_max) {
-  if (n == 0) return;
-  LK_REQUIRE(k >= 2 && k <= LETKF_B200_MAX_MEMBERS, "eigensolver: need 2 <= k <= 256");
-  const bool smem_ok = eig_smem_bytes<T>(k, true) <= 200 * 1024;
-  const size_t smem = eig_smem_bytes<T>(k, smem_ok);
+template <typename T, int MODE, int RPL>
+static void launch_rpl(cudaStream_t s, int k, int64_t n, T *Cio, const T *b, T *lam, T *wbar, const T *A, T *W,
+                       T *V, int32_t *sweeps_max) {
+  const int kp = (k + 7) & ~7;
+  const size_t smem_full = sizeof(T) * (3 * (size_t)kp + (size_t)kp * 32 * RPL);
+  const bool smem_ok = smem_full <= 220 * 1024;
+  LK_REQUIRE(smem_ok || k % 32 == 0,
+             "eigensolver: k above the shared-memory limit (160 FP64 / 224 FP32) must be a multiple of 32");
+  const size_t smem = smem_ok ? smem_full : sizeof(T) * 3 * (size_t)kp;
+  int nwarps = std::max(1, std::min(kp / 8, RPL >= 5 ? 8 : 16));
+  const int threads = 32 * nwarps;
   for (int64_t u0 = 0; u0 < n; u0 += 1 << 30) {
     const int64_t nu = std::min<int64_t>(n - u0, 1 << 30);
     const int64_t o2 = u0 * (int64_t)k * k, o1 = u0 * (int64_t)k;
     if (smem_ok) {
-      auto kern = eig_block_kernel<T, MODE, true>;
+      auto kern = eig_blk_kernel<T, MODE, RPL, true>;
       LK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      kern<<<(unsigned)nu, 256, smem, s>>>(k, nu, Cio ? Cio + o2 : nullptr, b ? b + o1 : nullptr,
-                                           lam ? lam + o1 : nullptr, wbar ? wbar + o1 : nullptr,
-                                           A ? A + o2 : nullptr, W ? W + o1 : nullptr, V ? V + o2 : nullptr,
-                                           sweeps_max);
+      kern<<<(unsigned)nu, threads, smem, s>>>(k, nu, Cio ? Cio + o2 : nullptr, b ? b + o1 : nullptr,
+                                               lam ? lam + o1 : nullptr, wbar ? wbar + o1 : nullptr,
+                                               A ? A + o2 : nullptr, W ? W + o1 : nullptr, V ? V + o2 : nullptr,
+                                               sweeps_max);
     } else {
-      auto kern = eig_block_kernel<T, MODE, false>;
-      kern<<<(unsigned)nu, 256, smem, s>>>(k, nu, Cio ? Cio + o2 : nullptr, b ? b + o1 : nullptr,
-                                           lam ? lam + o1 : nullptr, wbar ? wbar + o1 : nullptr,
-                                           A ? A + o2 : nullptr, W ? W + o1 : nullptr, V ? V + o2 : nullptr,
-                                           sweeps_max);
+      auto kern = eig_blk_kernel<T, MODE, RPL, false>;
+      kern<<<(unsigned)nu, threads, smem, s>>>(k, nu, Cio ? Cio + o2 : nullptr, b ? b + o1 : nullptr,
+                                               lam ? lam + o1 : nullptr, wbar ? wbar + o1 : nullptr,
+                                               A ? A + o2 : nullptr, W ? W + o1 : nullptr, V ? V + o2 : nullptr,
+                                               sweeps_max);
     }
     launch_counter()++;
   }
   LK_CUDA(cudaGetLastError());
+}
+
+template <typename T, int MODE>
+static void launch_eig_generic(cudaStream_t s, int k, int64_t n, T *Cio, const T *b, T *lam, T *wbar, const T *A,
+                               T *W, T *V, int32_t *sweeps_max) {
+  if (n == 0) return;
+  LK_REQUIRE(k >= 2 && k <= LETKF_B200_MAX_MEMBERS, "eigensolver: need 2 <= k <= 256");
+  const int rpl = (k + 31) / 32;
+  switch (rpl) {
+    case 1: launch_rpl<T, MODE, 1>(s, k, n, Cio, b, lam, wbar, A, W, V, sweeps_max); break;
+    case 2: launch_rpl<T, MODE, 2>(s, k, n, Cio, b, lam, wbar, A, W, V, sweeps_max); break;
+    case 3: launch_rpl<T, MODE, 3>(s, k, n, Cio, b, lam, wbar, A, W, V, sweeps_max); break;
+    case 4: launch_rpl<T, MODE, 4>(s, k, n, Cio, b, lam, wbar, A, W, V, sweeps_max); break;
+    case 5: launch_rpl<T, MODE, 5>(s, k, n, Cio, b, lam, wbar, A, W, V, sweeps_max); break;
+    case 6: launch_rpl<T, MODE, 6>(s, k, n, Cio, b, lam, wbar, A, W, V, sweeps_max); break;
+    case 7: launch_rpl<T, MODE, 7>(s, k, n, Cio, b, lam, wbar, A, W, V, sweeps_max); break;
+    default: launch_rpl<T, MODE, 8>(s, k, n, Cio, b, lam, wbar, A, W, V, sweeps_max); break;
+  }
 }
 
 template <typename T>

@@ -17,76 +17,12 @@
 // c = rsqrt(1 + t^2), s = c t delivers.
 #include <cstdlib>
 
-#include "letkf_internal.cuh"
+#include "eig_common.cuh"
 
 namespace lk {
 
 constexpr int K32 = 32;
 constexpr unsigned FULL = 0xffffffffu;
-
-__device__ __forceinline__ float rsqrt_approx(float x) {
-  float r;
-  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-  return r;
-}
-__device__ __forceinline__ float rcp_approx(float x) {
-  float r;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-  return r;
-}
-
-template <typename T>
-struct Fast;
-template <>
-struct Fast<double> {
-  static __device__ __forceinline__ double rsqrt(double x) {  // x > 0 within float range
-    double r = (double)rsqrt_approx((float)x);
-    const double h = 0.5 * x;
-    double e = fma(-h * r, r, 0.5);
-    r = fma(r, e, r);
-    e = fma(-h * r, r, 0.5);
-    r = fma(r, e, r);
-    return r;
-  }
-  static __device__ __forceinline__ double rcp(double x) {
-    float rf;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rf) : "f"((float)x));
-    double r = (double)rf;
-    double e = fma(-x, r, 1.0);
-    r = fma(r, e, r);
-    e = fma(-x, r, 1.0);
-    r = fma(r, e, r);
-    return r;
-  }
-  // one Newton step (relative error ~1e-13): enough for the rotation ANGLE, which only has to
-  // annihilate gamma approximately; c and s themselves use the full-accuracy rsqrt
-  static __device__ __forceinline__ double rsqrt1(double x) {
-    double r = (double)rsqrt_approx((float)x);
-    const double e = fma(-0.5 * x * r, r, 0.5);
-    return fma(r, e, r);
-  }
-  static __device__ __forceinline__ double rcp1(double x) {
-    float rf;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rf) : "f"((float)x));
-    double r = (double)rf;
-    const double e = fma(-x, r, 1.0);
-    return fma(r, fma(e, e, e), r);  // r (1 + e + e^2): one cubic step
-  }
-  static __device__ __forceinline__ double tol2(int k) { return 4.930380657631324e-32 * k; }  // (eps sqrt k)^2
-};
-template <>
-struct Fast<float> {
-  static __device__ __forceinline__ float rsqrt(float x) {
-    float r = rsqrt_approx(x);
-    const float h = 0.5f * x;
-    const float e = fmaf(-h * r, r, 0.5f);
-    return fmaf(r, e, r);
-  }
-  static __device__ __forceinline__ float rcp(float x) { return __frcp_rn(x); }
-  static __device__ __forceinline__ float rsqrt1(float x) { return rsqrt_approx(x); }
-  static __device__ __forceinline__ float rcp1(float x) { return __frcp_rn(x); }
-  static __device__ __forceinline__ float tol2(int k) { return 1.4210855e-14f * k; }
-};
 
 __host__ __device__ constexpr int rr_pos(int m) { return (m & 1) ? 31 - (m >> 1) : (m >> 1); }
 __host__ __device__ constexpr int rr_reg(int p) { return p <= 15 ? 2 * p : 2 * (31 - p) + 1; }
@@ -191,29 +127,8 @@ __device__ __forceinline__ int warp_jacobi32(T (&g)[K32], int lane, T *csbuf, T 
       const T g2 = gamma * gamma, ab = alpha * beta;
       const bool rot = g2 > tol2 * ab;
       big |= g2 > stop2 * ab;
-      T c = T(1), s = T(0), t = T(0);
-      {
-        const T delta = beta - alpha;
-        T tt;
-        if (FASTROT) {
-          const float df = (float)delta, gf = (float)gamma;
-          const float x = fmaxf(fmaf(df, df, 4.f * gf * gf), 1e-30f);
-          const float h = x * rsqrt_approx(x);
-          tt = (T)((df >= 0.f ? 2.f : -2.f) * gf * rcp_approx(fabsf(df) + h));
-        } else {
-          T x = fma(delta, delta, T(4) * g2);
-          x = rot ? x : T(1);
-          const T h = x * Fast<T>::rsqrt1(x);
-          const T den = fabs(delta) + h;
-          tt = (delta >= T(0) ? T(2) : T(-2)) * gamma * Fast<T>::rcp1(den);
-        }
-        const T cc = Fast<T>::rsqrt(fma(tt, tt, T(1)));
-        if (rot) {
-          t = tt;
-          c = cc;
-          s = cc * tt;
-        }
-      }
+      T c, s, t;
+      jacobi_rotation<T, FASTROT>(alpha, beta, gamma, rot, c, s, t);
       rotated |= rot;
       d = (lane & 1) ? fma(t, gamma, d) : fma(-t, gamma, d);  // beta + t gamma | alpha - t gamma
       if (!(lane & 1)) {
