@@ -166,3 +166,195 @@ template void launch_gram<float>(cudaStream_t, const TreeViews &, int, int64_t, 
                                  float *, float *, int32_t *);
 
 }  // namespace lk
+
+// =====================================================================================================
+// Tensor-core Gram for any k (FP64 accumulation on mma.sync.m8n8k4.f64), used for every k != 32.
+//
+// C is tiled in 8x8 MMA tiles grouped into 32x32 super-blocks; only the S(S+1)/2 lower super-blocks
+// (S = ceil(k/32)) are computed.  A warp owns up to two super-blocks (16 tiles = 32 accumulator doubles
+// each); a CTA of up to 8 warps owns up to 16 of them and a unit is spread over as many CTAs as
+// needed (k = 256: 36 super-blocks -> 3 CTAs).  Rows are staged 32 at a time as doubles in shared
+// memory with a row stride = 8 (mod 16) doubles, so that the fragment load of a 4-row group
+// (lane -> row lane%4, member 8I + lane/4) costs the minimal two wavefronts.  The same fragment is the
+// A operand of tile row I and the B operand of tile column I.
+// =====================================================================================================
+namespace lk {
+
+__device__ __forceinline__ void dmma884g(double &d0, double &d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(d0), "+d"(d1)
+               : "d"(a), "d"(b));
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+    gram_dmma_kernel(TreeViews tv, int k, int S, int sb_per_cta, int64_t nunits, const int32_t *__restrict__ unit_pt,
+                     double mu, T *__restrict__ C, T *__restrict__ bvec, int32_t *__restrict__ nanflag) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int KP = 32 * S;     // padded member count
+  const int LDS_ = KP + 8;   // row stride in doubles: 8 (mod 16)
+  double *yb_s = reinterpret_cast<double *>(smem_raw);  // [kRows][LDS_]
+  double *yo_s = yb_s + kRows * LDS_;                   // [kRows]
+  RowMeta *meta = reinterpret_cast<RowMeta *>(yo_s + kRows);
+  __shared__ int s_nan;
+  __shared__ unsigned s_pmask;
+
+  const int64_t unit = blockIdx.x;
+  if (unit >= nunits) return;
+  const int64_t q = unit_pt[unit];
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
+  const int lr = lane >> 2, lc = lane & 3;
+  const int NSB = S * (S + 1) / 2;
+  if (tid == 0) s_nan = 0;
+
+  // this warp's super-blocks (si >= sj), linear index over the lower triangle
+  int sbi[2], sbj[2];
+  bool has[2];
+#pragma unroll
+  for (int s = 0; s < 2; ++s) {
+    const int lin = blockIdx.y * sb_per_cta + warp * 2 + s;
+    has[s] = (warp * 2 + s) < sb_per_cta && lin < NSB;
+    int i = 0, rem = has[s] ? lin : 0;
+    while (rem > i) {
+      rem -= i + 1;
+      ++i;
+    }
+    sbi[s] = i;
+    sbj[s] = rem;
+  }
+  double acc[2][16][2];
+#pragma unroll
+  for (int s = 0; s < 2; ++s)
+#pragma unroll
+    for (int t = 0; t < 16; ++t) acc[s][t][0] = acc[s][t][1] = 0.0;
+  double bacc = 0.0;  // b[tid] for the CTA with blockIdx.y == 0
+
+  for (int t = 0; t < tv.ntrees; ++t) {
+    const TreeView &TV = tv.t[t];
+    const int ncand = TV.cnt[q] * TV.nact;
+    for (int c0 = 0; c0 < ncand; c0 += kRows) {
+      __syncthreads();
+      if (tid < kRows) {
+        RowMeta m;
+        m.pert = nullptr;
+        m.ei = 0.f;
+        m.yo = 0.f;
+        m.pass = 0;
+        const int c = c0 + tid;
+        if (c < ncand) {
+          const int j = c / TV.nact, a = c - j * TV.nact;
+          const int64_t o = (int64_t)(TV.idx[q * TV.nalloc + j] - 1) * TV.nvar + TV.act[a];
+          if (TV.pass[o]) {
+            m.pass = 1;
+            m.ei = lk_error_inv(TV.err[o], TV.r2[q * TV.nalloc + j], tv.weight_function);
+            m.yo = LK_MUL(TV.omm[o], m.ei);
+            m.pert = TV.pert + o * k;
+            if (m.ei != m.ei) s_nan = 1;
+          }
+        }
+        meta[tid] = m;
+        yo_s[tid] = (double)m.yo;
+        const unsigned pm = __ballot_sync(0xffffffffu, m.pass != 0);
+        if (tid == 0) s_pmask = pm;
+      }
+      __syncthreads();
+      const unsigned pmask = s_pmask;
+      for (int r = warp; r < kRows; r += nw) {
+        const RowMeta m = meta[r];
+        for (int i = lane; i < KP; i += 32) {
+          float v = 0.f;
+          if (m.pass && i < k) v = LK_MUL(__ldg(m.pert + i), m.ei);
+          yb_s[r * LDS_ + i] = (double)v;
+        }
+      }
+      __syncthreads();
+      if (blockIdx.y == 0 && tid < k) {
+#pragma unroll 8
+        for (int r = 0; r < kRows; ++r) bacc = fma(yb_s[r * LDS_ + tid], yo_s[r], bacc);
+      }
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+        if (!has[s]) continue;
+        const bool diag = sbi[s] == sbj[s];
+#pragma unroll 2
+        for (int g8 = 0; g8 < 8; ++g8) {
+          if (((pmask >> (4 * g8)) & 0xFu) == 0u) continue;
+          const double *row = yb_s + (4 * g8 + lc) * LDS_ + lr;
+          double fa[4], fb[4];
+#pragma unroll
+          for (int I = 0; I < 4; ++I) fa[I] = row[32 * sbi[s] + 8 * I];
+          if (diag) {
+#pragma unroll
+            for (int I = 0; I < 4; ++I) fb[I] = fa[I];
+          } else {
+#pragma unroll
+            for (int I = 0; I < 4; ++I) fb[I] = row[32 * sbj[s] + 8 * I];
+          }
+#pragma unroll
+          for (int I = 0; I < 4; ++I)
+#pragma unroll
+            for (int J = 0; J < 4; ++J) {
+              if (diag && J > I) continue;  // upper tiles of a diagonal super-block are not needed
+              dmma884g(acc[s][I * 4 + J][0], acc[s][I * 4 + J][1], fa[I], fb[J]);
+            }
+        }
+      }
+    }
+  }
+  __syncthreads();
+  T *Cu = C + unit * (int64_t)k * k;
+#pragma unroll
+  for (int s = 0; s < 2; ++s) {
+    if (!has[s]) continue;
+    const bool diag = sbi[s] == sbj[s];
+#pragma unroll
+    for (int I = 0; I < 4; ++I)
+#pragma unroll
+      for (int J = 0; J < 4; ++J) {
+        if (diag && J > I) continue;
+        const int row = 32 * sbi[s] + 8 * I + lr, col = 32 * sbj[s] + 8 * J + 2 * lc;
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int cc = col + e;
+          if (row < k && cc < k) {
+            const double v = acc[s][I * 4 + J][e] + (row == cc ? mu : 0.0);
+            // element (row, cc), row >= cc except inside diagonal tiles: store where the column-major
+            // lower triangle lives (and its mirror, so diagonal tiles are complete)
+            Cu[(int64_t)cc * k + row] = (T)v;
+            if (diag && I == J) Cu[(int64_t)row * k + cc] = (T)v;
+          }
+        }
+      }
+  }
+  if (blockIdx.y == 0) {
+    if (tid < k) bvec[unit * (int64_t)k + tid] = (T)bacc;
+    if (tid == 0) nanflag[unit] = s_nan;
+  }
+}
+
+template <typename T>
+void launch_gram_dmma(cudaStream_t s, const TreeViews &tv, int k, int64_t nunits, const int32_t *unit_pt, T mu,
+                      T *C, T *b, int32_t *nanflag) {
+  if (nunits == 0) return;
+  LK_REQUIRE(k <= LETKF_B200_MAX_MEMBERS, "launch_gram_dmma: nmember > 256");
+  const int S = (k + 31) / 32;
+  const int NSB = S * (S + 1) / 2;
+  const int ncta = (NSB + 15) / 16;
+  const int sb_per_cta = (NSB + ncta - 1) / ncta;
+  int nwarps = (sb_per_cta + 1) / 2;
+  nwarps = std::max(nwarps, (k + 31) / 32);  // the b-vector needs k threads in CTA 0
+  const size_t smem = sizeof(double) * ((size_t)kRows * (32 * S + 8) + kRows) + kRows * sizeof(RowMeta);
+  auto kern = gram_dmma_kernel<T>;
+  LK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<dim3((unsigned)nunits, (unsigned)ncta), 32 * nwarps, smem, s>>>(tv, k, S, sb_per_cta, nunits, unit_pt,
+                                                                          (double)mu, C, b, nanflag);
+  launch_counter()++;
+  LK_CUDA(cudaGetLastError());
+}
+template void launch_gram_dmma<double>(cudaStream_t, const TreeViews &, int, int64_t, const int32_t *, double,
+                                       double *, double *, int32_t *);
+template void launch_gram_dmma<float>(cudaStream_t, const TreeViews &, int, int64_t, const int32_t *, float, float *,
+                                      float *, int32_t *);
+
+}  // namespace lk

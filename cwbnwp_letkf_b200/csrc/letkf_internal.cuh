@@ -148,6 +148,10 @@ void launch_count_rows(cudaStream_t s, const TreeViews &tv, int64_t nq, int32_t 
 template <typename T>
 void launch_gram(cudaStream_t s, const TreeViews &tv, int k, int64_t nunits, const int32_t *unit_pt,
                  T mu, T *C /*[nunits][k][k]*/, T *b /*[nunits][k]*/, int32_t *nanflag);
+// tensor-core (FP64 mma) variant for any k; writes the column-major lower triangle of C
+template <typename T>
+void launch_gram_dmma(cudaStream_t s, const TreeViews &tv, int k, int64_t nunits, const int32_t *unit_pt, T mu,
+                      T *C, T *b, int32_t *nanflag);
 // C,b -> U (orthonormal eigenvectors, column-major), lam (unsorted), wbar = U diag(1/lam) U^T b
 template <typename T>
 void launch_eig_solve(cudaStream_t s, int k, int64_t nunits, T *C_inout_U, const T *b, T *lam,
