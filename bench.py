@@ -332,7 +332,8 @@ def main():
                  "unit": "TFLOP/s", "gathered_GBs": (4 * k + 8) * rows0 / (stats.ms_gram * 1e-3) / 1e9},
         "eigen": {"ms": stats.ms_eigen, "bound": "fp64", "achieved": 4.0 * k**3 * units / (stats.ms_eigen * 1e-3) / 1e12,
                   "peak": fma64, "unit": "TFLOP/s", "eigensolves_per_s": units / (stats.ms_eigen * 1e-3),
-                  "max_sweeps": stats.max_sweeps},
+                  "max_sweeps": stats.max_sweeps,
+                  "mean_sweeps": (stats.sweeps_sum / units) if units and stats.sweeps_sum else None},
         "transform": {"ms": stats.ms_transform, "bound": "hbm",
                       "achieved": 8.0 * k * units / (stats.ms_transform * 1e-3) / 1e9, "peak": None, "unit": "GB/s"},
         "tree_build_ms": stats.ms_tree,

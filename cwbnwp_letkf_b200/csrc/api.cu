@@ -424,10 +424,11 @@ static void run_pipeline(letkf_b200_ctx *c, const letkf_b200_var_config *cfg, in
     }
     if (cfg->tune_q && co.transform)
       for (int f = 0; f < nfields; ++f) launch_tune_q(s, k, npts, d_var + (int64_t)f * npts * k);  // core:252-278
-    int32_t h_sw = 0;
-    LK_CUDA(cudaMemcpyAsync(&h_sw, c->counters.p + 1, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    int32_t h_sw[2] = {0, 0};
+    LK_CUDA(cudaMemcpyAsync(h_sw, c->counters.p + 1, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
     LK_CUDA(cudaStreamSynchronize(s));
-    stats.max_sweeps = h_sw;
+    stats.max_sweeps = h_sw[0];
+    stats.sweeps_sum = h_sw[1];
   }
   LK_CUDA(cudaEventRecord(c->ev[7], s));
   LK_CUDA(cudaEventSynchronize(c->ev[7]));

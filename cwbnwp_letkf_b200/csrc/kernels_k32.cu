@@ -97,6 +97,10 @@ __global__ void __launch_bounds__(128)
         v.x = acc[tix][0] + (row == col ? mu : 0.0);
         v.y = acc[tix][1] + (row == col + 1 ? mu : 0.0);
         *reinterpret_cast<double2 *>(Cu + row * 32 + col) = v;
+        if (I != J) {  // mirror: the warm-started eigensolver multiplies with full rows of C
+          Cu[col * 32 + row] = v.x;
+          Cu[(col + 1) * 32 + row] = v.y;
+        }
         ++tix;
       }
   }

@@ -57,6 +57,7 @@ module letkf_b200
         integer(c_int64_t) :: npts, npts_analysed, rows, units
         integer(c_int32_t) :: ntrees, max_sweeps
         real(c_float)      :: ms_tree, ms_search, ms_gram, ms_eigen, ms_transform, ms_total
+        integer(c_int64_t) :: sweeps_sum
     end type letkf_b200_stats
 
     type(c_ptr), save :: ctx = c_null_ptr

@@ -48,7 +48,8 @@ class Stats(ctypes.Structure):
     _fields_ = [("npts", ctypes.c_int64), ("npts_analysed", ctypes.c_int64), ("rows", ctypes.c_int64),
                 ("units", ctypes.c_int64), ("ntrees", ctypes.c_int32), ("max_sweeps", ctypes.c_int32),
                 ("ms_tree", ctypes.c_float), ("ms_search", ctypes.c_float), ("ms_gram", ctypes.c_float),
-                ("ms_eigen", ctypes.c_float), ("ms_transform", ctypes.c_float), ("ms_total", ctypes.c_float)]
+                ("ms_eigen", ctypes.c_float), ("ms_transform", ctypes.c_float), ("ms_total", ctypes.c_float),
+                ("sweeps_sum", ctypes.c_int64)]
 
     def as_dict(self):
         return {f: getattr(self, f) for f, _ in self._fields_}

@@ -80,6 +80,7 @@ typedef struct {
   int32_t ntrees;
   int32_t max_sweeps;    /* largest Jacobi sweep count in the eigen stage */
   float ms_tree, ms_search, ms_gram, ms_eigen, ms_transform, ms_total; /* device time per stage */
+  int64_t sweeps_sum;    /* total Jacobi sweeps over all units (k = 32 path; 0 if not counted) */
 } letkf_b200_stats;
 
 typedef struct letkf_b200_ctx letkf_b200_ctx;
