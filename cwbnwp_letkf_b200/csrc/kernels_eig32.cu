@@ -296,18 +296,63 @@ __global__ void __launch_bounds__(128, MINB)
 // row-per-lane layout with the second operand broadcast from shared memory.
 // Shared memory per warp: A = U_prev (8 KB), B = scratch (T = C U_prev, U', and the Jacobi reduction
 // buffer), 64 values for (c,s).
-constexpr int LDA32 = 34;  // row stride of the U_prev buffer: 16-byte aligned rows, column reads 4-way at worst
+constexpr int LDA32 = 34;  // row stride of the shared-memory matrices: 16-byte aligned rows, <= 4-way conflicts
 
-template <typename T, int RUN>
+__device__ __forceinline__ void dmma884e(double &d0, double &d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(d0), "+d"(d1)
+               : "d"(a), "d"(b));
+}
+
+// 32x32x32 product on the FP64 tensor pipe: D = op(A) B with fragments fetched by the functors
+// fa(row, col) -> A[row][col], fb(row, col) -> B[row][col]; D is stored to `out` (row stride LDA32).
+// The tensor pipe is otherwise idle in this kernel, so these products overlap with the FP64-pipe
+// Jacobi work of the other resident warps.
+template <typename FA, typename FB>
+__device__ __forceinline__ void warp_gemm32_dmma(FA fa, FB fb, double *out, int lane) {
+  const int lr = lane >> 2, lc = lane & 3;
+  double acc[4][4][2];
+#pragma unroll
+  for (int I = 0; I < 4; ++I)
+#pragma unroll
+    for (int J = 0; J < 4; ++J) acc[I][J][0] = acc[I][J][1] = 0.0;
+#pragma unroll 2
+  for (int kk = 0; kk < 8; ++kk) {
+    double a[4], b[4];
+#pragma unroll
+    for (int I = 0; I < 4; ++I) a[I] = fa(8 * I + lr, 4 * kk + lc);
+#pragma unroll
+    for (int J = 0; J < 4; ++J) b[J] = fb(4 * kk + lc, 8 * J + lr);
+#pragma unroll
+    for (int I = 0; I < 4; ++I)
+#pragma unroll
+      for (int J = 0; J < 4; ++J) dmma884e(acc[I][J][0], acc[I][J][1], a[I], b[J]);
+  }
+  __syncwarp();  // every lane has finished reading the operands (out may alias one of them)
+#pragma unroll
+  for (int I = 0; I < 4; ++I)
+#pragma unroll
+    for (int J = 0; J < 4; ++J) {
+      double2 v;
+      v.x = acc[I][J][0];
+      v.y = acc[I][J][1];
+      *reinterpret_cast<double2 *>(out + (8 * I + lr) * LDA32 + 8 * J + 2 * lc) = v;
+    }
+  __syncwarp();
+}
+
+template <int RUN>
 __global__ void __launch_bounds__(128, 3)
-    eig32_chain_kernel(int64_t n, T *__restrict__ Cio, const T *__restrict__ bvec, T *__restrict__ lam,
-                       T *__restrict__ wbar, int32_t *__restrict__ sweeps_max, int32_t *__restrict__ sweeps_sum) {
+    eig32_chain_kernel(int64_t n, double *__restrict__ Cio, const double *__restrict__ bvec,
+                       double *__restrict__ lam, double *__restrict__ wbar, int32_t *__restrict__ sweeps_max,
+                       int32_t *__restrict__ sweeps_sum) {
+  using T = double;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  T *base = reinterpret_cast<T *>(smem_raw) + (size_t)w * (32 * LDA32 + 1024 + 64);
+  T *base = reinterpret_cast<T *>(smem_raw) + (size_t)w * (2 * 32 * LDA32 + 64);
   T *Abuf = base;                 // U_prev, [l][j] with row stride LDA32
-  T *Bbuf = base + 32 * LDA32;    // scratch, row-major stride 32
-  T *cs = Bbuf + 1024;            // 64
+  T *Bbuf = base + 32 * LDA32;    // scratch (T = C U_prev, C', U', Jacobi reduction buffer), stride LDA32
+  T *cs = Bbuf + 32 * LDA32;      // 64
   const int64_t u0 = ((int64_t)blockIdx.x * 4 + w) * RUN;
   if (u0 >= n) return;
   const int64_t u1 = u0 + RUN < n ? u0 + RUN : n;
@@ -318,31 +363,14 @@ __global__ void __launch_bounds__(128, 3)
     const T *Cu = Cio + u * (int64_t)(K32 * K32);
     T g[K32];
     if (warm) {
-      // T = C U_prev : t[j] = sum_l C[lane][l] A[l][j]; C[lane][l] = C[l][lane] is read coalesced
-      {
-        T t[K32];
+      // T = C U_prev  (C straight from global memory, L1/L2 resident)
+      warp_gemm32_dmma([&](int r, int c) { return Cu[r * K32 + c]; },
+                       [&](int r, int c) { return Abuf[r * LDA32 + c]; }, Bbuf, lane);
+      // C' = U_prev^T T   (written over T)
+      warp_gemm32_dmma([&](int r, int c) { return Abuf[c * LDA32 + r]; },
+                       [&](int r, int c) { return Bbuf[r * LDA32 + c]; }, Bbuf, lane);
 #pragma unroll
-        for (int j = 0; j < K32; ++j) t[j] = T(0);
-#pragma unroll 4
-        for (int l = 0; l < K32; ++l) {
-          const T cl = Cu[l * K32 + lane];
-#pragma unroll
-          for (int j = 0; j < K32; ++j) t[j] = fma(cl, Abuf[l * LDA32 + j], t[j]);
-        }
-        __syncwarp();
-#pragma unroll
-        for (int j = 0; j < K32; ++j) Bbuf[lane * 32 + j] = t[j];
-      }
-      __syncwarp();
-      // C' = U_prev^T T : g[j] = sum_l A[l][lane] B[l][j]
-#pragma unroll
-      for (int j = 0; j < K32; ++j) g[j] = T(0);
-#pragma unroll 4
-      for (int l = 0; l < K32; ++l) {
-        const T al = Abuf[l * LDA32 + lane];
-#pragma unroll
-        for (int j = 0; j < K32; ++j) g[j] = fma(al, Bbuf[l * 32 + j], g[j]);
-      }
+      for (int j = 0; j < K32; ++j) g[j] = Bbuf[lane * LDA32 + j];
       __syncwarp();
     } else {
 #pragma unroll
@@ -369,20 +397,19 @@ __global__ void __launch_bounds__(128, 3)
     for (int j = 0; j < K32; ++j) g[j] *= cs[j];  // row `lane` of U'
     __syncwarp();
     if (warm) {
-      // U = U_prev U' : new row i = sum_l A[i][l] U'[l][:]
+      // U = U_prev U'  (result lands in Abuf: it is the next U_prev)
 #pragma unroll
-      for (int j = 0; j < K32; ++j) Bbuf[lane * 32 + j] = g[j];
+      for (int j = 0; j < K32; ++j) Bbuf[lane * LDA32 + j] = g[j];
       __syncwarp();
+      warp_gemm32_dmma([&](int r, int c) { return Abuf[r * LDA32 + c]; },
+                       [&](int r, int c) { return Bbuf[r * LDA32 + c]; }, Abuf, lane);
 #pragma unroll
-      for (int j = 0; j < K32; ++j) g[j] = T(0);
-#pragma unroll 4
-      for (int l = 0; l < K32; ++l) {
-        const T al = Abuf[lane * LDA32 + l];
+      for (int j = 0; j < K32; ++j) g[j] = Abuf[lane * LDA32 + j];
+    } else {
 #pragma unroll
-        for (int j = 0; j < K32; ++j) g[j] = fma(al, Bbuf[l * 32 + j], g[j]);
-      }
-      __syncwarp();
+      for (int j = 0; j < K32; ++j) Abuf[lane * LDA32 + j] = g[j];
     }
+    __syncwarp();
     // a unit whose matrix is not finite / not positive (real32 Gaspari-Cohn NaN rows) must
     // not seed its neighbour
     prev_ok = !__any_sync(FULL, !(lambda > T(0)) || !(lambda < T(1e300)));
@@ -404,10 +431,7 @@ __global__ void __launch_bounds__(128, 3)
     __syncwarp();
     T *Uo = Cio + u * (int64_t)(K32 * K32) + (int64_t)lane * K32;
 #pragma unroll
-    for (int j = 0; j < K32; ++j) {
-      Uo[j] = g[j];
-      Abuf[lane * LDA32 + j] = g[j];  // becomes U_prev of the next unit
-    }
+    for (int j = 0; j < K32; ++j) Uo[j] = g[j];
     lam[u * K32 + lane] = lambda;
     wbar[u * K32 + lane] = wb;
     __syncwarp();
@@ -430,13 +454,16 @@ void launch_eig32_solve(cudaStream_t s, int64_t n, T *C_inout_U, const T *b, T *
     const char *e = getenv("LETKF_B200_EIG_CHAIN");
     return e ? atoi(e) : 16;
   }();
-  if (chain > 1) {
+  if (chain > 1 && sizeof(T) == 8) {
     constexpr int RUN = 16;
-    const size_t smem = sizeof(T) * 4 * (32 * LDA32 + 1024 + 64);
-    auto kern = eig32_chain_kernel<T, RUN>;
+    const size_t smem = sizeof(double) * 4 * (2 * 32 * LDA32 + 64);
+    auto kern = eig32_chain_kernel<RUN>;
     LK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t nwarp = (n + RUN - 1) / RUN;
-    kern<<<(unsigned)((nwarp + 3) / 4), 128, smem, s>>>(n, C_inout_U, b, lam, wbar, sweeps_max,
+    kern<<<(unsigned)((nwarp + 3) / 4), 128, smem, s>>>(n, reinterpret_cast<double *>(C_inout_U),
+                                                         reinterpret_cast<const double *>(b),
+                                                         reinterpret_cast<double *>(lam),
+                                                         reinterpret_cast<double *>(wbar), sweeps_max,
                                                          sweeps_max ? sweeps_max + 1 : nullptr);
     launch_counter()++;
     LK_CUDA(cudaGetLastError());
