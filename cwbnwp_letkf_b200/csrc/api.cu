@@ -33,6 +33,7 @@ struct letkf_b200_ctx {
   cudaEvent_t ev[8] = {};
   std::map<std::pair<int, int>, std::unique_ptr<ObsDev>> obs;  // (family, type), iteration = reference order
   int64_t chunk_override = 0;
+  int nz_hint = 1;             // letkf_b200_set_levels: points p and p + l*(npts/nz) share (x, y)
   bool force_generic = false;  // LETKF_B200_GENERIC=1: use the generic block-per-unit kernels for every k
   // per-call device staging for the host-pointer entry points
   DevBuf<float> d_xyz, d_var;
@@ -97,6 +98,11 @@ extern "C" int letkf_b200_finalize(letkf_b200_ctx *c) {
 
 extern "C" int64_t letkf_b200_launch_count(letkf_b200_ctx *) { return launch_counter(); }
 extern "C" void *letkf_b200_stream(letkf_b200_ctx *c) { return c ? (void *)c->stream : nullptr; }
+extern "C" int letkf_b200_set_levels(letkf_b200_ctx *c, int nz) {
+  if (!c || nz < 1) return 1;
+  c->nz_hint = nz;
+  return 0;
+}
 extern "C" int letkf_b200_set_chunk(letkf_b200_ctx *c, int64_t n) {
   if (!c || n < 0) return 1;
   c->chunk_override = n;
@@ -335,7 +341,15 @@ static void run_pipeline(letkf_b200_ctx *c, const letkf_b200_var_config *cfg, in
   LK_CUDA(cudaEventRecord(c->ev[1], s));
   float ms_search = 0, ms_gram = 0, ms_eig = 0, ms_xf = 0;
   if (!act.empty() && npts > 0) {  // core:66: nothing to do without trees
-    const int64_t chunk = pick_chunk(c, act, npts, sizeof(T));
+    // When every active type is localised in 2-D only, the local observation lists -- hence Yb, C and
+    // the weights -- depend on (x, y) alone: all levels of a column share them.  With the level count
+    // declared (letkf_b200_set_levels) the search / Gram / eigen stages run once per column and only the
+    // transform runs per point.  Same arithmetic on the same inputs as solving every level: exact.
+    bool all2d = true;
+    for (auto &a : act) all2d = all2d && a.dim == 2;
+    const int nz = (all2d && c->nz_hint > 1 && npts % c->nz_hint == 0 && !co.p && !co.wbar && !co.Wa) ? c->nz_hint : 1;
+    const int64_t nsearch = npts / nz;  // columns (or all points)
+    const int64_t chunk = pick_chunk(c, act, nsearch, sizeof(T));
     TreeViews tv = make_views(c, cfg, act, chunk);
     c->p.ensure(chunk);
     c->unit_pt.ensure(chunk);
@@ -350,8 +364,8 @@ static void run_pipeline(letkf_b200_ctx *c, const letkf_b200_var_config *cfg, in
     LK_CUDA(cudaMemsetAsync(c->counters.p, 0, 4 * sizeof(int32_t), s));
     const float inflat = LK_DIV((float)(k - 1), cfg->multi_infl);  // core:68 (real32)
     const T mu = (T)inflat;                                       // core:645
-    for (int64_t c0 = 0; c0 < npts; c0 += chunk) {
-      const int64_t nq = std::min(chunk, npts - c0);
+    for (int64_t c0 = 0; c0 < nsearch; c0 += chunk) {
+      const int64_t nq = std::min(chunk, nsearch - c0);
       LK_CUDA(cudaEventRecord(c->ev[2], s));
       for (int t = 0; t < tv.ntrees; ++t) launch_search(s, tv.t[t], nq, d_xyz + c0 * 3);
       launch_count_rows(s, tv, nq, c->p.p);
@@ -367,9 +381,9 @@ static void run_pipeline(letkf_b200_ctx *c, const letkf_b200_var_config *cfg, in
       LK_CUDA(cudaMemcpyAsync(&h_rows, c->rows_sum.p, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
       LK_CUDA(cudaStreamSynchronize(s));
       const int64_t nunits = h_cnt[0];
-      stats.npts_analysed += nunits;
+      stats.npts_analysed += nunits * nz;
       stats.units += nunits;
-      stats.rows += h_rows;
+      stats.rows += h_rows * nz;
       if (co.p) LK_CUDA(cudaMemcpyAsync(co.p + c0, c->p.p, sizeof(int32_t) * nq, cudaMemcpyDeviceToDevice, s));
       if (nunits > 0) {
         c->C.ensure((size_t)nunits * k * k * sizeof(T));
@@ -401,12 +415,15 @@ static void run_pipeline(letkf_b200_ctx *c, const letkf_b200_var_config *cfg, in
             launch_weights_dump<T>(s, k, nunits, c->unit_pt.p, C, lam, wbar, wo, Wo);
         }
         if (co.transform && nfields > 0) {
-          if (fast32)
-            launch_transform32<T>(s, nunits, c->unit_pt.p, npts, c0, C, lam, wbar, c->nanflag.p, nfields, d_var,
+          for (int l = 0; l < nz; ++l) {  // nz > 1: the same weights serve every level of the column
+            const int64_t base = c0 + (int64_t)l * nsearch;
+            if (fast32)
+              launch_transform32<T>(s, nunits, c->unit_pt.p, npts, base, C, lam, wbar, c->nanflag.p, nfields, d_var,
+                                    cfg->use_rtpp, cfg->rtpp_alpha, cfg->use_rtps, cfg->rtps_alpha, co.xa_raw);
+            else
+              launch_transform<T>(s, k, nunits, c->unit_pt.p, npts, base, C, lam, wbar, c->nanflag.p, nfields, d_var,
                                   cfg->use_rtpp, cfg->rtpp_alpha, cfg->use_rtps, cfg->rtps_alpha, co.xa_raw);
-          else
-            launch_transform<T>(s, k, nunits, c->unit_pt.p, npts, c0, C, lam, wbar, c->nanflag.p, nfields, d_var,
-                                cfg->use_rtpp, cfg->rtpp_alpha, cfg->use_rtps, cfg->rtps_alpha, co.xa_raw);
+          }
         }
         LK_CUDA(cudaEventRecord(c->ev[6], s));
         LK_CUDA(cudaEventSynchronize(c->ev[6]));

@@ -60,7 +60,8 @@ EXPORTS = ["letkf_b200_init", "letkf_b200_finalize", "letkf_b200_last_error", "l
            "letkf_b200_analyze_dev", "letkf_b200_tune_q", "letkf_b200_tune_q_dev", "letkf_b200_search",
            "letkf_b200_yoyb", "letkf_b200_weights", "letkf_b200_syevd_batched",
            "letkf_b200_syevd_batched_dev", "letkf_b200_fma_peak", "letkf_b200_launch_count",
-           "letkf_b200_stream", "letkf_b200_set_chunk", "letkf_b200_selftest_host_search"]
+           "letkf_b200_stream", "letkf_b200_set_chunk", "letkf_b200_set_levels",
+           "letkf_b200_selftest_host_search"]
 
 
 def library_path() -> str:
@@ -99,6 +100,7 @@ def load_library():
     L.letkf_b200_stream.argtypes = [vp]
     L.letkf_b200_stream.restype = vp
     L.letkf_b200_set_chunk.argtypes = [vp, i64]
+    L.letkf_b200_set_levels.argtypes = [vp, i32]
     L.letkf_b200_selftest_host_search.argtypes = [i32, vp, ctypes.c_float, ctypes.c_float, i64, vp, i32, vp,
                                                   vp, vp, vp, vp]
     _LIB = L
@@ -152,6 +154,10 @@ class LetkfB200:
     @property
     def stream_ptr(self) -> int:
         return int(self.L.letkf_b200_stream(self.h) or 0)
+
+    def set_levels(self, nz: int):
+        """Declare npts = ncol*nz (levels slowest) so that 2-D localised variables share weights per column."""
+        self._chk(self.L.letkf_b200_set_levels(self.h, int(nz)))
 
     def set_chunk(self, n: int):
         self._chk(self.L.letkf_b200_set_chunk(self.h, int(n)))

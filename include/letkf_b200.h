@@ -184,6 +184,13 @@ int letkf_b200_selftest_host_search(int n, const float *obs_xyz, float hclr, flo
 int64_t letkf_b200_launch_count(letkf_b200_ctx *ctx);
 /* stream the library launches on (cudaStream_t), for CUDA-event timing by the caller */
 void *letkf_b200_stream(letkf_b200_ctx *ctx);
+/* Declares the vertical structure of the grid handed to analyze: npts = ncol*nz with point
+ * p + l*ncol directly above point p (the memory order of var(loc_nx,loc_ny,nz,:), core:85).  When
+ * every active observation type of a variable is localised in 2-D only (vclr <= 0 -- MU, P, PH in
+ * input.nml:45-46,52,...), all levels of a column have the same local observations and weights; the
+ * library then searches / solves once per column and only transforms per point.  nz = 1 (default)
+ * disables the sharing. */
+int letkf_b200_set_levels(letkf_b200_ctx *ctx, int nz);
 /* tuning knob: points per pipeline chunk (0 = automatic) */
 int letkf_b200_set_chunk(letkf_b200_ctx *ctx, int64_t chunk_points);
 

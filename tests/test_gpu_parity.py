@@ -253,6 +253,32 @@ def test_mixed_dimension_family_is_refused_like_the_oracle():
         eng.get_lz(C.sample_namelist("T", use_gpspw=True), sc.xyz_grid)
 
 
+def test_column_sharing_for_2d_variables_is_exact():
+    """P is localised in 2-D only (input.nml): with the level count declared, search / Gram / eigen run
+    once per column.  The arithmetic is the same as solving every point; only the warm-start partner of
+    the eigensolver differs, so results agree to working-precision rounding (real32 output: >= 99 %
+    bit-identical, the rest within one ulp)."""
+    sc, rng = S.scenario_tiny(k=32)
+    cfg = C.sample_namelist("P")
+    eng, _ = _engines(sc)
+    f = S.make_field(rng, sc.k, sc.xyz_grid, 1000.0, 50.0, 2.0)
+    a = f.copy()
+    st_a = eng.analyze(cfg, sc.xyz_grid, a)
+    eng.set_levels(sc.nz)
+    b = f.copy()
+    st_b = eng.analyze(cfg, sc.xyz_grid, b)
+    assert (a == b).mean() > 0.99 and np.abs(a - b).max() <= 2.5e-7 * np.abs(a).max()
+    assert st_b.units * sc.nz == st_a.units and st_b.npts_analysed == st_a.npts_analysed and st_b.rows == st_a.rows
+    # a 3-D localised variable ignores the hint
+    cfg3 = C.sample_namelist("T")
+    c3 = f.copy()
+    eng.analyze(cfg3, sc.xyz_grid, c3)
+    eng.set_levels(1)
+    d3 = f.copy()
+    eng.analyze(cfg3, sc.xyz_grid, d3)
+    assert np.array_equal(c3, d3)
+
+
 def test_chunking_is_invisible():
     sc, rng = S.scenario_tiny(k=8)
     cfg = C.sample_namelist("T")
