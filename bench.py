@@ -313,6 +313,7 @@ def main():
         e2e = {"value": total_pts / (ms_e / a.steps * 1e-3), "unit": "grid points/s",
                "h2d_bytes_per_step": int(total_pts * (3 + k) * 4),
                "d2h_bytes_per_step": int(total_pts * k * 4), "ms_per_step": ms_e / a.steps,
+               "pipeline_ms_inside": eng.last_stats.ms_total,
                "matches_resident_path": same}
 
     if rank != 0:

@@ -37,6 +37,10 @@ struct letkf_b200_ctx {
   bool force_generic = false;  // LETKF_B200_GENERIC=1: use the generic block-per-unit kernels for every k
   // per-call device staging for the host-pointer entry points
   DevBuf<float> d_xyz, d_var;
+  // double-buffered slabs + copy streams of the pipelined host-pointer analyze
+  DevBuf<float> slab_xyz[2], slab_var[2];
+  cudaStream_t cs_in = nullptr, cs_out = nullptr;
+  cudaEvent_t ev_in[2] = {}, ev_done[2] = {}, ev_out[2] = {};
   // per-chunk scratch
   DevBuf<int32_t> cnt[LETKF_B200_MAX_TYPES], idx[LETKF_B200_MAX_TYPES];
   DevBuf<float> r2[LETKF_B200_MAX_TYPES];
@@ -92,6 +96,15 @@ extern "C" int letkf_b200_finalize(letkf_b200_ctx *c) {
     for (auto &ev : c->ev)
       if (ev) cudaEventDestroy(ev);
     cudaStreamDestroy(c->stream);
+    if (c->cs_in) {
+      cudaStreamDestroy(c->cs_in);
+      cudaStreamDestroy(c->cs_out);
+      for (int i = 0; i < 2; ++i) {
+        cudaEventDestroy(c->ev_in[i]);
+        cudaEventDestroy(c->ev_done[i]);
+        cudaEventDestroy(c->ev_out[i]);
+      }
+    }
     delete c;
   });
 }
@@ -476,6 +489,12 @@ extern "C" int letkf_b200_analyze_dev(letkf_b200_ctx *c, const letkf_b200_var_co
   return guarded([&] { analyze_dev_impl(c, cfg, npts, xyz, nfields, var, st); });
 }
 
+// Host-pointer entry point.  By default the whole grid is copied in, analysed and copied out (on a
+// B200 host the two transfers of config M cost ~60 ms of a 1.4 s step).  With LETKF_B200_SLAB=<points>
+// the grid is instead streamed through double-buffered slabs (slab i+1 copied in and slab i-1 copied
+// out on two copy streams while slab i is analysed) -- for grids that do not fit in HBM; measured
+// slower than the single pass when everything fits (per-slab overheads > hidden copy time).  Points
+// are independent, so slabbing does not change results.
 extern "C" int letkf_b200_analyze(letkf_b200_ctx *c, const letkf_b200_var_config *cfg, int64_t npts,
                                   const float *xyz, int nfields, float *var, letkf_b200_stats *st) {
   return guarded([&] {
@@ -483,14 +502,79 @@ extern "C" int letkf_b200_analyze(letkf_b200_ctx *c, const letkf_b200_var_config
     LK_REQUIRE(npts >= 0 && nfields >= 0, "negative size");
     LK_REQUIRE(npts == 0 || (xyz && (nfields == 0 || var)), "null array");
     LK_CUDA(cudaSetDevice(c->device));
-    const size_t nv = (size_t)npts * c->k * nfields;
-    c->d_xyz.ensure((size_t)npts * 3 + 1);
-    c->d_var.ensure(nv + 1);
-    LK_CUDA(cudaMemcpyAsync(c->d_xyz.p, xyz, sizeof(float) * 3 * npts, cudaMemcpyHostToDevice, c->stream));
-    LK_CUDA(cudaMemcpyAsync(c->d_var.p, var, sizeof(float) * nv, cudaMemcpyHostToDevice, c->stream));
-    analyze_dev_impl(c, cfg, npts, c->d_xyz.p, nfields, c->d_var.p, st);
-    LK_CUDA(cudaMemcpyAsync(var, c->d_var.p, sizeof(float) * nv, cudaMemcpyDeviceToHost, c->stream));
+    const int k = c->k;
+    int64_t slab = (int64_t)1 << 40;
+    if (const char *e = getenv("LETKF_B200_SLAB"))  // test knob; values <= 0 keep the default
+      if (atoll(e) > 0) slab = std::max<int64_t>(32, atoll(e));
+    if (npts <= slab + slab / 2 || c->nz_hint > 1) {  // small grid, or whole columns needed: one piece
+      const size_t nv = (size_t)npts * k * nfields;
+      c->d_xyz.ensure((size_t)npts * 3 + 1);
+      c->d_var.ensure(nv + 1);
+      LK_CUDA(cudaMemcpyAsync(c->d_xyz.p, xyz, sizeof(float) * 3 * npts, cudaMemcpyHostToDevice, c->stream));
+      LK_CUDA(cudaMemcpyAsync(c->d_var.p, var, sizeof(float) * nv, cudaMemcpyHostToDevice, c->stream));
+      analyze_dev_impl(c, cfg, npts, c->d_xyz.p, nfields, c->d_var.p, st);
+      LK_CUDA(cudaMemcpyAsync(var, c->d_var.p, sizeof(float) * nv, cudaMemcpyDeviceToHost, c->stream));
+      LK_CUDA(cudaStreamSynchronize(c->stream));
+      return;
+    }
+    const int rows = nfields * k;  // field f, member m is row f*k+m of a [rows][npts] host matrix
+    if (!c->cs_in) {
+      LK_CUDA(cudaStreamCreateWithFlags(&c->cs_in, cudaStreamNonBlocking));
+      LK_CUDA(cudaStreamCreateWithFlags(&c->cs_out, cudaStreamNonBlocking));
+      for (int i = 0; i < 2; ++i) {
+        LK_CUDA(cudaEventCreateWithFlags(&c->ev_in[i], cudaEventDisableTiming));
+        LK_CUDA(cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming));
+        LK_CUDA(cudaEventCreateWithFlags(&c->ev_out[i], cudaEventDisableTiming));
+      }
+    }
+    for (int i = 0; i < 2; ++i) {
+      c->slab_xyz[i].ensure((size_t)slab * 3);
+      c->slab_var[i].ensure((size_t)slab * rows + 1);
+    }
+    const int64_t nslab = (npts + slab - 1) / slab;
+    auto copy_in = [&](int64_t i) {
+      const int b = (int)(i & 1);
+      const int64_t s0 = i * slab, ns = std::min(slab, npts - s0);
+      if (i >= 2) LK_CUDA(cudaStreamWaitEvent(c->cs_in, c->ev_out[b], 0));  // buffer b drained by slab i-2
+      LK_CUDA(cudaMemcpyAsync(c->slab_xyz[b].p, xyz + s0 * 3, sizeof(float) * 3 * ns, cudaMemcpyHostToDevice, c->cs_in));
+      if (rows > 0)
+        LK_CUDA(cudaMemcpy2DAsync(c->slab_var[b].p, sizeof(float) * ns, var + s0, sizeof(float) * npts,
+                                  sizeof(float) * ns, rows, cudaMemcpyHostToDevice, c->cs_in));
+      LK_CUDA(cudaEventRecord(c->ev_in[b], c->cs_in));
+    };
+    letkf_b200_stats tot;
+    std::memset(&tot, 0, sizeof(tot));
+    copy_in(0);
+    for (int64_t i = 0; i < nslab; ++i) {
+      const int b = (int)(i & 1);
+      const int64_t s0 = i * slab, ns = std::min(slab, npts - s0);
+      if (i + 1 < nslab) copy_in(i + 1);
+      LK_CUDA(cudaStreamWaitEvent(c->stream, c->ev_in[b], 0));
+      letkf_b200_stats one;
+      analyze_dev_impl(c, cfg, ns, c->slab_xyz[b].p, nfields, c->slab_var[b].p, &one);
+      LK_CUDA(cudaEventRecord(c->ev_done[b], c->stream));
+      LK_CUDA(cudaStreamWaitEvent(c->cs_out, c->ev_done[b], 0));
+      if (rows > 0)
+        LK_CUDA(cudaMemcpy2DAsync(var + s0, sizeof(float) * npts, c->slab_var[b].p, sizeof(float) * ns,
+                                  sizeof(float) * ns, rows, cudaMemcpyDeviceToHost, c->cs_out));
+      LK_CUDA(cudaEventRecord(c->ev_out[b], c->cs_out));
+      tot.npts += one.npts;
+      tot.npts_analysed += one.npts_analysed;
+      tot.rows += one.rows;
+      tot.units += one.units;
+      tot.ntrees = one.ntrees;
+      tot.max_sweeps = std::max(tot.max_sweeps, one.max_sweeps);
+      tot.sweeps_sum += one.sweeps_sum;
+      tot.ms_tree += one.ms_tree;
+      tot.ms_search += one.ms_search;
+      tot.ms_gram += one.ms_gram;
+      tot.ms_eigen += one.ms_eigen;
+      tot.ms_transform += one.ms_transform;
+      tot.ms_total += one.ms_total;
+    }
+    LK_CUDA(cudaStreamSynchronize(c->cs_out));
     LK_CUDA(cudaStreamSynchronize(c->stream));
+    if (st) *st = tot;
   });
 }
 

@@ -279,6 +279,21 @@ def test_column_sharing_for_2d_variables_is_exact():
     assert np.array_equal(c3, d3)
 
 
+def test_pipelined_slabs_are_invisible(monkeypatch):
+    """The host-pointer call streams large grids through double-buffered slabs; force tiny slabs."""
+    sc, rng = S.scenario_tiny(k=32)
+    cfg = C.sample_namelist("T")
+    eng, _ = _engines(sc)
+    f = np.stack([S.make_field(rng, sc.k, sc.xyz_grid, 280.0, 5.0, 1.0) for _ in range(2)])
+    a = f.copy()
+    st_a = eng.analyze(cfg, sc.xyz_grid, a)
+    monkeypatch.setenv("LETKF_B200_SLAB", "100")
+    b = f.copy()
+    st_b = eng.analyze(cfg, sc.xyz_grid, b)
+    assert st_a.npts_analysed == st_b.npts_analysed and st_a.rows == st_b.rows and st_b.npts == sc.npts
+    assert (a == b).mean() > 0.99 and np.abs(a - b).max() <= 2.5e-7 * np.abs(a).max()
+
+
 def test_chunking_is_invisible():
     sc, rng = S.scenario_tiny(k=8)
     cfg = C.sample_namelist("T")
