@@ -94,9 +94,17 @@ __host__ __device__ __forceinline__ int search_one(const KdNodeDev *__restrict__
       }
       cur = closer;
     }
-    // terminal node: scan the bucket in storage order (kd2:1654-1707)
-    for (int i = l; i <= u; ++i) {
-      const float4 p = ld_ro(pts + i);
+    // terminal node: scan the bucket in storage order (kd2:1654-1707).  A bucket holds at most 13
+    // points (kd2:505,737); all of them are fetched first so that the loads are in flight together
+    // (the scan itself has data-dependent exits, which would otherwise serialise 13 L2 round trips).
+    float4 pv[13];
+#pragma unroll
+    for (int j = 0; j < 13; ++j)
+      if (l + j <= u) pv[j] = ld_ro(pts + l + j);
+#pragma unroll
+    for (int j = 0; j < 13; ++j) {
+      if (l + j > u) break;
+      const float4 p = pv[j];
       float d = LK_SUB(p.x, q0);
       float sd = LK_MUL(d, d);
       if (sd > r2) continue;
