@@ -307,6 +307,42 @@ def test_chunking_is_invisible():
     assert np.array_equal(a, b)
 
 
+# ------------------------------------------------------------------------------ properties at scale
+def test_size_independent_properties_on_a_large_grid():
+    """No oracle at this size (0.9 M points, 10^5 radar + GTS obs): properties the LETKF update has for
+    any input.  (1) points without local obs are untouched and the analysed count is consistent;
+    (2) the update is equivariant under a constant shift of the background (weights do not depend on
+    the field); (3) RTPP with alpha = 1 restores the background perturbations, so only the ensemble
+    mean moves; (4) every analysed point keeps a finite ensemble."""
+    rng = np.random.default_rng(8)
+    sc = S.Scenario("big", 150, 150, 40, 32, 2000.0, S.make_grid(150, 150, 40, 2000.0))
+    S.add_gts(sc, rng)
+    S.add_radar(sc, rng, 60_000, 40_000, n_sites=3, radius=60e3)
+    eng = H.LetkfB200(sc.k, True)
+    for o in sc.obs.values():
+        eng.set_obs(o)
+    cfg = C.sample_namelist("QRAIN")
+    cfg.tune_q = False
+    f = S.make_field(rng, sc.k, sc.xyz_grid, 3.0, 1.0, 0.5)
+    a = f.copy()
+    st = eng.analyze(cfg, sc.xyz_grid, a)
+    changed = (a != f).any(0)
+    assert 0 < st.npts_analysed < sc.npts and changed.sum() <= st.npts_analysed
+    assert changed.sum() > 0.95 * st.npts_analysed and np.isfinite(a).all()
+    # (2) shift equivariance, to real32 rounding of values of size ~100
+    b = (f + np.float32(100.0)).astype(np.float32)
+    eng.analyze(cfg, sc.xyz_grid, b)
+    assert np.abs((b - np.float32(100.0)) - a).max() < 2e-4
+    # (3) RTPP alpha = 1, no RTPS: perturbations are those of the background
+    cfg1 = C.sample_namelist("QRAIN")
+    cfg1.tune_q, cfg1.use_rtps, cfg1.rtpp_alpha = False, False, 1.0
+    c = f.copy()
+    eng.analyze(cfg1, sc.xyz_grid, c)
+    pc, pf = c - c.mean(0, keepdims=True), f - f.mean(0, keepdims=True)
+    assert np.abs(pc - pf).max() < 5e-6
+    assert np.abs(c.mean(0) - f.mean(0))[changed].max() > 1e-3           # the mean did move
+
+
 # ------------------------------------------------------------------------------ eigensolver
 def _letkf_like(rng, b, k, p, dtype):
     Y = rng.normal(size=(b, k, p))
