@@ -9,6 +9,7 @@
 #include <cstring>
 
 #include "letkf_internal.cuh"
+#include "xform32.cuh"
 
 using namespace lk;
 
@@ -414,8 +415,14 @@ static void run_pipeline(letkf_b200_ctx *c, const letkf_b200_var_config *cfg, in
         else
           launch_gram<T>(s, tv, k, nunits, c->unit_pt.p, mu, C, b, c->nanflag.p);
         LK_CUDA(cudaEventRecord(c->ev[4], s));
+        // k = 32 FP64 with one transform per unit and no parity dump: the transform runs in the
+        // eigensolver's epilogue and U never leaves the registers
+        const bool fuse = fast32 && sizeof(T) == 8 && nz == 1 && co.transform && nfields > 0 && !co.wbar &&
+                          !co.Wa && eig32_can_fuse();
+        Xform32Args xargs{c->unit_pt.p, c->nanflag.p, npts, c0, nfields, d_var, cfg->use_rtpp, cfg->rtpp_alpha,
+                          cfg->use_rtps, cfg->rtps_alpha, co.xa_raw};
         if (fast32)
-          launch_eig32_solve<T>(s, nunits, C, b, lam, wbar, c->counters.p + 1);
+          launch_eig32_solve<T>(s, nunits, C, b, lam, wbar, c->counters.p + 1, fuse ? &xargs : nullptr);
         else
           launch_eig_solve<T>(s, k, nunits, C, b, lam, wbar, c->counters.p + 1);
         LK_CUDA(cudaEventRecord(c->ev[5], s));
@@ -427,7 +434,7 @@ static void run_pipeline(letkf_b200_ctx *c, const letkf_b200_var_config *cfg, in
           else
             launch_weights_dump<T>(s, k, nunits, c->unit_pt.p, C, lam, wbar, wo, Wo);
         }
-        if (co.transform && nfields > 0) {
+        if (co.transform && nfields > 0 && !fuse) {
           for (int l = 0; l < nz; ++l) {  // nz > 1: the same weights serve every level of the column
             const int64_t base = c0 + (int64_t)l * nsearch;
             if (fast32)

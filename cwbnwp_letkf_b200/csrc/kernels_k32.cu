@@ -10,7 +10,7 @@
 // transform32: xa = xb_mean + xb'.wbar + sqrt(k-1) U Lambda^(-1/2) U^T xb' with lane i holding row i
 // of U (the layout eig32 writes), one transposed butterfly for U^T xb' and a shared-memory
 // broadcast for the second product; RTPP/RTPS exactly as kernels_xform.cu.
-#include "letkf_internal.cuh"
+#include "xform32.cuh"
 
 namespace lk {
 
@@ -124,103 +124,23 @@ void launch_gram32(cudaStream_t s, const TreeViews &tv, int64_t nunits, const in
 }
 
 // ---- transform, k = 32 ------------------------------------------------------------------------------
-template <typename T, int N>
-__device__ __forceinline__ void treduce(T (&v)[N], int lane) {
-#pragma unroll
-  for (int n = N, mask = 16; n > 1; n >>= 1, mask >>= 1) {
-    const bool up = lane & mask;
-#pragma unroll
-    for (int i = 0; i < n / 2; ++i) {
-      const T send = up ? v[i] : v[i + n / 2];
-      const T keep = up ? v[i + n / 2] : v[i];
-      v[i] = keep + __shfl_xor_sync(FULLM, send, mask);
-    }
-  }
-}
-
-template <typename T>
-__device__ __forceinline__ T wsum(T v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULLM, v, o);
-  return v;
-}
-
-// sequential (member 0..31) real32 sum of one value per lane, as the oracle defines sum()
-__device__ __forceinline__ float seq_sum32(float v) {
-  float s = 0.f;
-#pragma unroll
-  for (int m = 0; m < 32; ++m) s = LK_ADD(s, __shfl_sync(FULLM, v, m));
-  return s;
-}
-
 template <typename T>
 __global__ void __launch_bounds__(128)
-    transform32_kernel(int64_t nunits, const int32_t *__restrict__ unit_pt, int64_t npts_total, int64_t pt_base,
-                       const T *__restrict__ U, const T *__restrict__ lam, const T *__restrict__ wbar,
-                       const int32_t *__restrict__ nanflag, int nfields, float *__restrict__ var, int use_rtpp,
-                       float rtpp_alpha, int use_rtps, float rtps_alpha, double *__restrict__ xa_raw) {
+    transform32_kernel(int64_t nunits, const T *__restrict__ U, const T *__restrict__ lam,
+                       const T *__restrict__ wbar, Xform32Args xa) {
   __shared__ __align__(16) T sbuf[4][32];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int64_t unit = (int64_t)blockIdx.x * 4 + w;
   if (unit >= nunits) return;
-  T *buf = sbuf[w];
-  const int64_t pt = pt_base + unit_pt[unit];
+  const int64_t pt = xa.pt_base + xa.unit_pt[unit];
   T u[32];
   {
     const T *Uu = U + unit * 1024 + (int64_t)lane * 32;
 #pragma unroll
     for (int j = 0; j < 32; ++j) u[j] = Uu[j];
   }
-  const T sk = sqrt((T)31);
-  const T scale = sk / sqrt(lam[unit * 32 + lane]);  // lane j: sqrt(k-1)/sqrt(lambda_j)
-  const T wb = wbar[unit * 32 + lane];
-  const bool isnan_unit = nanflag[unit] != 0;
-  const float ninv = LK_DIV(1.0f, 32.0f);
-
-  for (int f = 0; f < nfields; ++f) {
-    float *v = var + (int64_t)f * npts_total * 32;
-    const float xb = v[(int64_t)lane * npts_total + pt];                 // core:228
-    const T xmean = (T)LK_MUL(seq_sum32(xb), ninv);                       // core:671 (real32)
-    const T xp = (T)xb - xmean;                                           // core:672
-    const T sdot = wsum(xp * wb);
-    T pr[32];
-#pragma unroll
-    for (int j = 0; j < 32; ++j) pr[j] = u[j] * xp;
-    treduce<T, 32>(pr, lane);                                             // lane j: (U^T xb')_j
-    __syncwarp();
-    buf[lane] = pr[0] * scale;
-    __syncwarp();
-    T y = 0;
-#pragma unroll
-    for (int j = 0; j < 32; ++j) y = fma(u[j], buf[j], y);
-    T xa = xmean + (sdot + y);                                            // core:673-675
-    if (isnan_unit) xa = xa * T(NAN);
-    if (xa_raw) xa_raw[pt * 32 + lane] = (double)xa;
-    float xa32 = (float)xa;                                               // core:679
-    if (use_rtpp || use_rtps) {                                           // core:684-698
-      const float xa_mean = LK_MUL(seq_sum32(xa32), ninv);
-      float xap = LK_SUB(xa32, xa_mean);
-      if (use_rtpp) {
-        const float t1 = LK_MUL(LK_SUB(1.0f, rtpp_alpha), xap);
-        xap = (float)((T)t1 + (T)rtpp_alpha * xp);
-      }
-      if (use_rtps) {
-        // dot_product(xb',xb') in working precision, sequential like the oracle
-        T d = 0;
-#pragma unroll
-        for (int m = 0; m < 32; ++m) {
-          const T x = __shfl_sync(FULLM, xp, m);
-          d += x * x;
-        }
-        const float xb_std = (float)d;
-        const float xa_std = seq_sum32(LK_MUL(xap, xap));
-        const float fac = LK_ADD(LK_SUB(LK_MUL(rtps_alpha, LK_SQRT(LK_DIV(xb_std, xa_std))), rtps_alpha), 1.0f);
-        xap = LK_MUL(xap, fac);
-      }
-      xa32 = LK_ADD(xa_mean, xap);                                        // core:697
-    }
-    v[(int64_t)lane * npts_total + pt] = xa32;                            // core:229
-  }
+  const T scale = sqrt((T)31) / sqrt(lam[unit * 32 + lane]);  // lane j: sqrt(k-1)/sqrt(lambda_j)
+  transform32_unit<T>(u, scale, wbar[unit * 32 + lane], xa.nanflag[unit] != 0, pt, xa, sbuf[w], lane);
 }
 
 template <typename T>
@@ -228,9 +148,8 @@ void launch_transform32(cudaStream_t s, int64_t nunits, const int32_t *unit_pt, 
                         const T *U, const T *lam, const T *wbar, const int32_t *nanflag, int nfields, float *var,
                         int use_rtpp, float rtpp_alpha, int use_rtps, float rtps_alpha, double *xa_raw) {
   if (nunits == 0 || nfields == 0) return;
-  transform32_kernel<T><<<(unsigned)((nunits + 3) / 4), 128, 0, s>>>(nunits, unit_pt, npts_total, pt_base, U, lam,
-                                                                      wbar, nanflag, nfields, var, use_rtpp,
-                                                                      rtpp_alpha, use_rtps, rtps_alpha, xa_raw);
+  Xform32Args xa{unit_pt, nanflag, npts_total, pt_base, nfields, var, use_rtpp, rtpp_alpha, use_rtps, rtps_alpha, xa_raw};
+  transform32_kernel<T><<<(unsigned)((nunits + 3) / 4), 128, 0, s>>>(nunits, U, lam, wbar, xa);
   launch_counter()++;
   LK_CUDA(cudaGetLastError());
 }

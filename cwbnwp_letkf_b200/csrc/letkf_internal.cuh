@@ -175,8 +175,13 @@ double run_fma_peak(cudaStream_t s, int kind);
 // ---- k = 32 fast paths (warp per analysis unit; U stored by rows: U[i][j] at i*32+j) ----------
 void launch_gram32(cudaStream_t s, const TreeViews &tv, int64_t nunits, const int32_t *unit_pt, double mu,
                    double *C, double *b, int32_t *nanflag);
+struct Xform32Args;
+// fuse != nullptr: apply the transform in the solver's epilogue (FP64 chained kernel only); U/lam/wbar are
+// then not written
 template <typename T>
-void launch_eig32_solve(cudaStream_t s, int64_t n, T *C_inout_U, const T *b, T *lam, T *wbar, int32_t *sweeps_max);
+void launch_eig32_solve(cudaStream_t s, int64_t n, T *C_inout_U, const T *b, T *lam, T *wbar, int32_t *sweeps_max,
+                        const Xform32Args *fuse);
+bool eig32_can_fuse();
 template <typename T>
 void launch_syevd32(cudaStream_t s, int64_t n, const T *A, T *W, T *V, int32_t *sweeps_max);
 template <typename T>
