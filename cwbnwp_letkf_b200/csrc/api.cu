@@ -407,6 +407,18 @@ static void run_pipeline(letkf_b200_ctx *c, const letkf_b200_var_config *cfg, in
         T *C = reinterpret_cast<T *>(c->C.p), *b = reinterpret_cast<T *>(c->b.p);
         T *lam = reinterpret_cast<T *>(c->lam.p), *wbar = reinterpret_cast<T *>(c->wbar.p);
         const bool fast32 = k == 32 && !c->force_generic;  // warp-per-unit register kernels
+        // k = 32 FP64 with one transform per unit and no parity dump: the transform runs in the
+        // eigensolver's epilogue and U never leaves the registers
+        const bool fuse = fast32 && sizeof(T) == 8 && nz == 1 && co.transform && nfields > 0 && !co.wbar &&
+                          !co.Wa && eig32_can_fuse();
+        Xform32Args xargs{c->unit_pt.p, c->nanflag.p, npts, c0, nfields, d_var, cfg->use_rtpp, cfg->rtpp_alpha,
+                          cfg->use_rtps, cfg->rtps_alpha, co.xa_raw};
+        if (fuse && letkf32_fuse_all()) {
+          // everything after the search in one kernel (Gram on the tensor pipe overlaps Jacobi on the FP64 pipe)
+          launch_letkf32_fused(s, tv, nunits, (double)mu, xargs, c->counters.p + 1);
+          LK_CUDA(cudaEventRecord(c->ev[4], s));
+          LK_CUDA(cudaEventRecord(c->ev[5], s));
+        } else {
         if (fast32 && sizeof(T) == 8)
           launch_gram32(s, tv, nunits, c->unit_pt.p, (double)mu, reinterpret_cast<double *>(C),
                         reinterpret_cast<double *>(b), c->nanflag.p);
@@ -415,12 +427,6 @@ static void run_pipeline(letkf_b200_ctx *c, const letkf_b200_var_config *cfg, in
         else
           launch_gram<T>(s, tv, k, nunits, c->unit_pt.p, mu, C, b, c->nanflag.p);
         LK_CUDA(cudaEventRecord(c->ev[4], s));
-        // k = 32 FP64 with one transform per unit and no parity dump: the transform runs in the
-        // eigensolver's epilogue and U never leaves the registers
-        const bool fuse = fast32 && sizeof(T) == 8 && nz == 1 && co.transform && nfields > 0 && !co.wbar &&
-                          !co.Wa && eig32_can_fuse();
-        Xform32Args xargs{c->unit_pt.p, c->nanflag.p, npts, c0, nfields, d_var, cfg->use_rtpp, cfg->rtpp_alpha,
-                          cfg->use_rtps, cfg->rtps_alpha, co.xa_raw};
         if (fast32)
           launch_eig32_solve<T>(s, nunits, C, b, lam, wbar, c->counters.p + 1, fuse ? &xargs : nullptr);
         else
@@ -444,6 +450,7 @@ static void run_pipeline(letkf_b200_ctx *c, const letkf_b200_var_config *cfg, in
               launch_transform<T>(s, k, nunits, c->unit_pt.p, npts, base, C, lam, wbar, c->nanflag.p, nfields, d_var,
                                   cfg->use_rtpp, cfg->rtpp_alpha, cfg->use_rtps, cfg->rtps_alpha, co.xa_raw);
           }
+        }
         }
         LK_CUDA(cudaEventRecord(c->ev[6], s));
         LK_CUDA(cudaEventSynchronize(c->ev[6]));

@@ -182,6 +182,10 @@ template <typename T>
 void launch_eig32_solve(cudaStream_t s, int64_t n, T *C_inout_U, const T *b, T *lam, T *wbar, int32_t *sweeps_max,
                         const Xform32Args *fuse);
 bool eig32_can_fuse();
+// k = 32 FP64: Gram + eigen + transform of a chunk in ONE kernel (C, U stay on chip)
+void launch_letkf32_fused(cudaStream_t s, const TreeViews &tv, int64_t n, double mu, const Xform32Args &xa,
+                          int32_t *sweeps_max);
+bool letkf32_fuse_all();
 template <typename T>
 void launch_syevd32(cudaStream_t s, int64_t n, const T *A, T *W, T *V, int32_t *sweeps_max);
 template <typename T>
