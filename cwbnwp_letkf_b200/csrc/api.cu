@@ -422,8 +422,16 @@ static void run_pipeline(letkf_b200_ctx *c, const letkf_b200_var_config *cfg, in
         if (fast32 && sizeof(T) == 8)
           launch_gram32(s, tv, nunits, c->unit_pt.p, (double)mu, reinterpret_cast<double *>(C),
                         reinterpret_cast<double *>(b), c->nanflag.p);
-        else if (!c->force_generic && !(fast32 && sizeof(T) == 4))
-          launch_gram_dmma<T>(s, tv, k, nunits, c->unit_pt.p, mu, C, b, c->nanflag.p);
+        else if (!c->force_generic && !(fast32 && sizeof(T) == 4)) {
+          static const bool use_tma = [] {
+            const char *e = getenv("LETKF_B200_GRAM_TMA");
+            return !e || atoi(e) != 0;
+          }();
+          if (use_tma && k % 4 == 0)
+            launch_gram_tma<T>(s, tv, k, nunits, c->unit_pt.p, mu, C, b, c->nanflag.p);
+          else
+            launch_gram_dmma<T>(s, tv, k, nunits, c->unit_pt.p, mu, C, b, c->nanflag.p);
+        }
         else
           launch_gram<T>(s, tv, k, nunits, c->unit_pt.p, mu, C, b, c->nanflag.p);
         LK_CUDA(cudaEventRecord(c->ev[4], s));

@@ -358,3 +358,264 @@ template void launch_gram_dmma<float>(cudaStream_t, const TreeViews &, int, int6
                                       float *, int32_t *);
 
 }  // namespace lk
+
+// =====================================================================================================
+// TMA-staged variant of the tensor-core Gram (k % 4 == 0).  The rows of a batch are 4k-byte contiguous
+// lines of the ob-major perturbation table; one elected thread gathers them with 1-D bulk asynchronous
+// copies (cp.async.bulk.shared.global, completion on an mbarrier) into a double-buffered shared-memory
+// stage, so the gather of batch i+1 is in flight while batch i feeds the tensor pipe.  Rows are kept as
+// the raw real32 perturbations (row stride 4k+32 bytes: the 4 rows of an MMA fragment fall in distinct
+// bank groups); yb = pert*error_inv (single real32 rounding) and the promotion to double happen in
+// registers when a fragment is loaded, so there is no separate conversion pass.
+// =====================================================================================================
+namespace lk {
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+struct RowMeta2 {
+  float ei, yo;
+  int pass;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+    gram_tma_kernel(TreeViews tv, int k, int S, int sb_per_cta, int64_t nunits, const int32_t *__restrict__ unit_pt,
+                    double mu, T *__restrict__ C, T *__restrict__ bvec, int32_t *__restrict__ nanflag) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int rowb = 4 * k + 32;  // bytes per staged row
+  unsigned char *stage0 = smem_raw;
+  unsigned char *stage1 = smem_raw + (size_t)kRows * rowb;
+  RowMeta2 *meta = reinterpret_cast<RowMeta2 *>(smem_raw + (size_t)2 * kRows * rowb);  // [2][kRows]
+  __shared__ __align__(8) uint64_t bars[2];
+  __shared__ int s_nan;
+  __shared__ unsigned s_pmask[2];
+  __shared__ int s_more[2];
+
+  const int64_t unit = blockIdx.x;
+  if (unit >= nunits) return;
+  const int64_t q = unit_pt[unit];
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int lr = lane >> 2, lc = lane & 3;
+  const int NSB = S * (S + 1) / 2;
+  if (tid == 0) {
+    s_nan = 0;
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  int sbi[2], sbj[2];
+  bool has[2];
+#pragma unroll
+  for (int s = 0; s < 2; ++s) {
+    const int lin = blockIdx.y * sb_per_cta + warp * 2 + s;
+    has[s] = (warp * 2 + s) < sb_per_cta && lin < NSB;
+    int i = 0, rem = has[s] ? lin : 0;
+    while (rem > i) {
+      rem -= i + 1;
+      ++i;
+    }
+    sbi[s] = i;
+    sbj[s] = rem;
+  }
+  double acc[2][16][2];
+#pragma unroll
+  for (int s = 0; s < 2; ++s)
+#pragma unroll
+    for (int t = 0; t < 16; ++t) acc[s][t][0] = acc[s][t][1] = 0.0;
+  double bacc = 0.0;
+  __syncthreads();
+
+  // batch iterator state (identical in every thread): tree index and candidate offset
+  int it_t = 0, it_c0 = 0;
+  auto advance_to_valid = [&]() {  // skip exhausted / empty trees
+    while (it_t < tv.ntrees && it_c0 >= tv.t[it_t].cnt[q] * tv.t[it_t].nact) {
+      ++it_t;
+      it_c0 = 0;
+    }
+  };
+  // warp 0 prepares batch `slot`: row metadata + the bulk copies of its passing rows
+  auto produce = [&](int slot) {
+    if (warp != 0) return;
+    const TreeView &TV = tv.t[it_t];
+    const int ncand = TV.cnt[q] * TV.nact;
+    RowMeta2 m{0.f, 0.f, 0};
+    const float *src = nullptr;
+    const int c = it_c0 + lane;
+    if (c < ncand) {
+      const int j = c / TV.nact, a = c - j * TV.nact;
+      const int64_t o = (int64_t)(TV.idx[q * TV.nalloc + j] - 1) * TV.nvar + TV.act[a];
+      if (TV.pass[o]) {
+        m.pass = 1;
+        m.ei = lk_error_inv(TV.err[o], TV.r2[q * TV.nalloc + j], tv.weight_function);
+        m.yo = LK_MUL(TV.omm[o], m.ei);
+        src = TV.pert + o * k;
+        if (m.ei != m.ei) s_nan = 1;
+      }
+    }
+    meta[slot * kRows + lane] = m;
+    const unsigned pm = __ballot_sync(0xffffffffu, m.pass != 0);
+    if (lane == 0) {
+      s_pmask[slot] = pm;
+      mbar_expect_tx(&bars[slot], (uint32_t)(__popc(pm) * 4 * k));
+    }
+    __syncwarp();
+    if (m.pass) tma_bulk_g2s((slot ? stage1 : stage0) + (size_t)lane * rowb, src, (uint32_t)(4 * k), &bars[slot]);
+  };
+
+  advance_to_valid();
+  bool more = it_t < tv.ntrees;
+  if (more) produce(0);
+  int slot = 0;
+  uint32_t phase[2] = {0u, 0u};
+  while (more) {
+    // position of the NEXT batch
+    int nt_t = it_t, nt_c0 = it_c0 + kRows;
+    {
+      const int sv_t = it_t, sv_c0 = it_c0;
+      it_t = nt_t;
+      it_c0 = nt_c0;
+      advance_to_valid();
+      nt_t = it_t;
+      nt_c0 = it_c0;
+      it_t = sv_t;
+      it_c0 = sv_c0;
+    }
+    const bool next_more = nt_t < tv.ntrees;
+    if (next_more) {  // prefetch the next batch into the other stage (its previous contents were consumed
+      it_t = nt_t;    // before the __syncthreads at the end of the previous iteration)
+      it_c0 = nt_c0;
+      produce(slot ^ 1);
+    }
+    __syncthreads();  // metadata of `slot` visible to all
+    mbar_wait(&bars[slot], phase[slot]);
+    phase[slot] ^= 1u;
+    const unsigned pmask = s_pmask[slot];
+    const unsigned char *st = slot ? stage1 : stage0;
+    const RowMeta2 *mt = meta + slot * kRows;
+    if (blockIdx.y == 0 && tid < k) {
+#pragma unroll 4
+      for (int r = 0; r < kRows; ++r) {
+        if (!((pmask >> r) & 1u)) continue;
+        const float v = LK_MUL(*reinterpret_cast<const float *>(st + (size_t)r * rowb + 4 * tid), mt[r].ei);
+        bacc = fma((double)v, (double)mt[r].yo, bacc);
+      }
+    }
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      if (!has[s]) continue;
+      const bool diag = sbi[s] == sbj[s];
+#pragma unroll 2
+      for (int g8 = 0; g8 < 8; ++g8) {
+        if (((pmask >> (4 * g8)) & 0xFu) == 0u) continue;
+        const int r = 4 * g8 + lc;
+        const bool ok = (pmask >> r) & 1u;
+        const float e = mt[r].ei;
+        const float *row = reinterpret_cast<const float *>(st + (size_t)r * rowb) + lr;
+        double fa[4], fb[4];
+#pragma unroll
+        for (int I = 0; I < 4; ++I) {
+          const int m = 32 * sbi[s] + 8 * I;
+          fa[I] = (ok && m + lr < k) ? (double)LK_MUL(row[m], e) : 0.0;
+        }
+        if (diag) {
+#pragma unroll
+          for (int I = 0; I < 4; ++I) fb[I] = fa[I];
+        } else {
+#pragma unroll
+          for (int I = 0; I < 4; ++I) {
+            const int m = 32 * sbj[s] + 8 * I;
+            fb[I] = (ok && m + lr < k) ? (double)LK_MUL(row[m], e) : 0.0;
+          }
+        }
+#pragma unroll
+        for (int I = 0; I < 4; ++I)
+#pragma unroll
+          for (int J = 0; J < 4; ++J) {
+            if (diag && J > I) continue;
+            dmma884g(acc[s][I * 4 + J][0], acc[s][I * 4 + J][1], fa[I], fb[J]);
+          }
+      }
+    }
+    __syncthreads();  // stage `slot` fully consumed: it may be refilled by the next produce()
+    more = next_more;
+    slot ^= 1;
+  }
+  T *Cu = C + unit * (int64_t)k * k;
+#pragma unroll
+  for (int s = 0; s < 2; ++s) {
+    if (!has[s]) continue;
+    const bool diag = sbi[s] == sbj[s];
+#pragma unroll
+    for (int I = 0; I < 4; ++I)
+#pragma unroll
+      for (int J = 0; J < 4; ++J) {
+        if (diag && J > I) continue;
+        const int row = 32 * sbi[s] + 8 * I + lr, col = 32 * sbj[s] + 8 * J + 2 * lc;
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int cc = col + e;
+          if (row < k && cc < k) {
+            const double v = acc[s][I * 4 + J][e] + (row == cc ? mu : 0.0);
+            Cu[(int64_t)cc * k + row] = (T)v;
+            if (diag && I == J) Cu[(int64_t)row * k + cc] = (T)v;
+          }
+        }
+      }
+  }
+  if (blockIdx.y == 0) {
+    if (tid < k) bvec[unit * (int64_t)k + tid] = (T)bacc;
+    if (tid == 0) nanflag[unit] = s_nan;
+  }
+}
+
+template <typename T>
+void launch_gram_tma(cudaStream_t s, const TreeViews &tv, int k, int64_t nunits, const int32_t *unit_pt, T mu, T *C,
+                     T *b, int32_t *nanflag) {
+  if (nunits == 0) return;
+  LK_REQUIRE(k <= LETKF_B200_MAX_MEMBERS && k % 4 == 0, "launch_gram_tma: k must be a multiple of 4, <= 256");
+  const int S = (k + 31) / 32;
+  const int NSB = S * (S + 1) / 2;
+  const int ncta = (NSB + 15) / 16;
+  const int sb_per_cta = (NSB + ncta - 1) / ncta;
+  int nwarps = (sb_per_cta + 1) / 2;
+  nwarps = std::max(nwarps, (k + 31) / 32);
+  const size_t smem = (size_t)2 * kRows * (4 * k + 32) + 2 * kRows * sizeof(RowMeta2);
+  auto kern = gram_tma_kernel<T>;
+  LK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<dim3((unsigned)nunits, (unsigned)ncta), 32 * nwarps, smem, s>>>(tv, k, S, sb_per_cta, nunits, unit_pt,
+                                                                          (double)mu, C, b, nanflag);
+  launch_counter()++;
+  LK_CUDA(cudaGetLastError());
+}
+template void launch_gram_tma<double>(cudaStream_t, const TreeViews &, int, int64_t, const int32_t *, double, double *,
+                                      double *, int32_t *);
+template void launch_gram_tma<float>(cudaStream_t, const TreeViews &, int, int64_t, const int32_t *, float, float *,
+                                     float *, int32_t *);
+
+}  // namespace lk

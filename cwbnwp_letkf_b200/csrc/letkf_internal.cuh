@@ -152,6 +152,10 @@ void launch_gram(cudaStream_t s, const TreeViews &tv, int k, int64_t nunits, con
 template <typename T>
 void launch_gram_dmma(cudaStream_t s, const TreeViews &tv, int k, int64_t nunits, const int32_t *unit_pt, T mu,
                       T *C, T *b, int32_t *nanflag);
+// same with the rows gathered by TMA bulk copies into a double-buffered stage (k % 4 == 0)
+template <typename T>
+void launch_gram_tma(cudaStream_t s, const TreeViews &tv, int k, int64_t nunits, const int32_t *unit_pt, T mu, T *C,
+                     T *b, int32_t *nanflag);
 // C,b -> U (orthonormal eigenvectors, column-major), lam (unsorted), wbar = U diag(1/lam) U^T b
 template <typename T>
 void launch_eig_solve(cudaStream_t s, int k, int64_t nunits, T *C_inout_U, const T *b, T *lam,
