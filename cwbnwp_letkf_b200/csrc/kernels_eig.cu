@@ -18,6 +18,8 @@
 // the exact column norms.  Within a round the 4 inner products are summed with one transposed
 // butterfly so that every 8-lane group ends up with one gamma and computes one rotation; squared
 // norms are carried in shared memory with the rotation update formulas.
+#include <cstdlib>
+
 #include "eig_common.cuh"
 
 namespace lk {
@@ -240,39 +242,113 @@ __device__ int block_jacobi_rb(T *G, int k, int kp, int ld, int nrows, T *nrm, T
   return sweeps;
 }
 
-// mode 0: LETKF solve.  in: C (full symmetric, SPD), b.  out: U (column-major, in place of C), lam, wbar.
+__device__ __forceinline__ void dmma884b(double &d0, double &d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(d0), "+d"(d1)
+               : "d"(a), "d"(b));
+}
+
+// kp x kp product D = A B on the FP64 tensor pipe by the whole CTA (kp % 16 == 0, at most 4 blocks of
+// 16x16 outputs per warp).  fa(i,l) -> A[i][l], fb(l,j) -> B[l][j] as double (0 outside k).  The result
+// is stored column-major to Gout (leading dimension ld), which may alias an operand: all operands are
+// read before the first store.
+template <typename T, typename FA, typename FB>
+__device__ __forceinline__ void block_gemm_dmma(FA fa, FB fb, T *Gout, int ld, int kp) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  const int lr = lane >> 2, lc = lane & 3;
+  const int nb16 = kp / 16, nblk = nb16 * nb16;
+  double acc[4][4][2];
+#pragma unroll
+  for (int bi = 0; bi < 4; ++bi) {
+#pragma unroll
+    for (int t = 0; t < 4; ++t) acc[bi][t][0] = acc[bi][t][1] = 0.0;
+    const int blk = warp + bi * nw;
+    if (blk < nblk) {
+      const int br = 16 * (blk / nb16), bc = 16 * (blk % nb16);
+#pragma unroll 2
+      for (int kk = 0; kk < kp; kk += 4) {
+        const double a0 = fa(br + lr, kk + lc), a1 = fa(br + 8 + lr, kk + lc);
+        const double b0 = fb(kk + lc, bc + lr), b1 = fb(kk + lc, bc + 8 + lr);
+        dmma884b(acc[bi][0][0], acc[bi][0][1], a0, b0);
+        dmma884b(acc[bi][1][0], acc[bi][1][1], a0, b1);
+        dmma884b(acc[bi][2][0], acc[bi][2][1], a1, b0);
+        dmma884b(acc[bi][3][0], acc[bi][3][1], a1, b1);
+      }
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int bi = 0; bi < 4; ++bi) {
+    const int blk = warp + bi * nw;
+    if (blk < nblk) {
+      const int br = 16 * (blk / nb16), bc = 16 * (blk % nb16);
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const int row = br + 8 * (t >> 1) + lr, col = bc + 8 * (t & 1) + 2 * lc;
+        Gout[row + (size_t)col * ld] = (T)acc[bi][t][0];
+        Gout[row + (size_t)(col + 1) * ld] = (T)acc[bi][t][1];
+      }
+    }
+  }
+  __syncthreads();
+}
+
+// mode 0: LETKF solve.  in: C (column-major lower triangle, SPD), b.  out: U (column-major, in place of C), lam, wbar.
 // mode 1: ?syevd.      in: A (lower).                  out: W ascending, V.
 template <typename T, int MODE, int RPL, bool SMEM>
 __global__ void __launch_bounds__(RPL >= 5 ? 256 : 512)
-    eig_blk_kernel(int k, int64_t n, T *__restrict__ Cio, const T *__restrict__ bvec, T *__restrict__ lam,
+    eig_blk_kernel(int k, int64_t n, int run, T *__restrict__ Cio, const T *__restrict__ bvec, T *__restrict__ lam,
                    T *__restrict__ wbar, const T *__restrict__ Ain, T *__restrict__ Wout, T *__restrict__ Vout,
-                   int32_t *__restrict__ sweeps_max) {
+                   int32_t *__restrict__ sweeps_max, int32_t *__restrict__ sweeps_sum) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T *sm = reinterpret_cast<T *>(smem_raw);
-  const int64_t u = blockIdx.x;
-  if (u >= n) return;
+  const int64_t u0 = (int64_t)blockIdx.x * run;
+  if (u0 >= n) return;
+  const int64_t u1 = u0 + run < n ? u0 + run : n;
   const int tid = threadIdx.x, nt = blockDim.x;
   const int warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
   const int kp = (k + 7) & ~7;
-  const int ld = SMEM ? 32 * RPL : k;  // in-place global storage requires k % 32 == 0 (checked on the host)
+  // shared-memory columns are padded by 4 rows: fragment loads of the warm-start products then spread
+  // over the banks; in-place global storage requires k % 32 == 0 (checked on the host)
+  const int ld = SMEM ? 32 * RPL + 4 : k;
   T *vec1 = sm;             // [kp]
   T *vec2 = sm + kp;        // [kp]
   T *nrm = sm + 2 * kp;     // [kp]
   T *Gs = sm + 3 * kp;      // [kp * ld] when SMEM
-  T *Gg = MODE == 0 ? Cio + u * (int64_t)k * k : Vout + u * (int64_t)k * k;
-  T *G = SMEM ? Gs : Gg;
   __shared__ T s_shift;
   __shared__ T red_lo[512], red_sc[512];
+  // Warm start (MODE 0, shared-memory path, kp % 16 == 0, <= 4 output blocks per warp): the CTA walks
+  // `run` consecutive units and solves each in the eigenbasis of the previous one, exactly as the k = 32
+  // chained kernel does; U_prev is read back from global memory (L2), the three products run on the
+  // FP64 tensor pipe.
+  const bool can_chain = MODE == 0 && SMEM && run > 1 && kp % 16 == 0 && (kp / 16) * (kp / 16) <= 4 * nw;
+  bool prev_ok = false;
 
   if (SMEM) {
-    for (int e = tid; e < kp * ld; e += nt) G[e] = T(0);
+    for (int e = tid; e < kp * ld; e += nt) Gs[e] = T(0);
     __syncthreads();
   }
+  for (int64_t u = u0; u < u1; ++u) {
+  T *Gg = MODE == 0 ? Cio + u * (int64_t)k * k : Vout + u * (int64_t)k * k;
+  T *G = SMEM ? Gs : Gg;
+  const bool warm = can_chain && prev_ok;
+  const T *Up = MODE == 0 && u > u0 ? Cio + (u - 1) * (int64_t)k * k : nullptr;  // U of the previous unit
   if (MODE == 0) {
-    if (SMEM)
-      for (int e = tid; e < k * k; e += nt) G[(e % k) + (size_t)(e / k) * ld] = Gg[e];
+    __syncthreads();
+    if (SMEM)  // Gram kernels deliver the column-major lower triangle: symmetrise while loading
+      for (int e = tid; e < k * k; e += nt) {
+        const int i = e % k, j = e / k;
+        G[i + (size_t)j * ld] = i >= j ? Gg[i + (size_t)j * k] : Gg[j + (size_t)i * k];
+      }
     if (tid == 0) s_shift = T(0);
     __syncthreads();
+    if (warm) {
+      // T = C U_prev, then C' = U_prev^T T (both written over G)
+      block_gemm_dmma<T>([&](int i, int l) { return (double)G[i + (size_t)l * ld]; },
+                         [&](int l, int j) { return (l < k && j < k) ? (double)Up[l + (size_t)j * k] : 0.0; }, G, ld, kp);
+      block_gemm_dmma<T>([&](int i, int l) { return (l < k && i < k) ? (double)Up[l + (size_t)i * k] : 0.0; },
+                         [&](int l, int j) { return (double)G[l + (size_t)j * ld]; }, G, ld, kp);
+    }
     block_cholesky(G, k, ld);  // C is SPD by construction; a NaN input propagates
   } else {
     const T *A = Ain + u * (int64_t)k * k;
@@ -321,6 +397,7 @@ __global__ void __launch_bounds__(RPL >= 5 ? 256 : 512)
   const T stop2 = MODE == 0 ? T(1e-14) : (sizeof(T) == 8 ? T(1e-18) : T(1e-9));
   const int sweeps = block_jacobi_rb<T, RPL, MODE == 0>(G, k, kp, ld, k, nrm, stop2);
   if (tid == 0 && sweeps_max) atomicMax(sweeps_max, sweeps);
+  if (tid == 0 && sweeps_sum) atomicAdd(sweeps_sum, sweeps);
 
   // column norms -> eigenvalues; normalise columns -> eigenvectors
   for (int j = warp; j < k; j += nw) {
@@ -335,6 +412,17 @@ __global__ void __launch_bounds__(RPL >= 5 ? 256 : 512)
   __syncthreads();
 
   if (MODE == 0) {
+    if (warm) {
+      // U = U_prev U'
+      block_gemm_dmma<T>([&](int i, int l) { return (i < k && l < k) ? (double)Up[i + (size_t)l * k] : 0.0; },
+                         [&](int l, int j) { return (double)G[l + (size_t)j * ld]; }, G, ld, kp);
+    }
+    {
+      // a unit whose matrix is not finite / not positive must not seed its neighbour
+      int bad = 0;
+      for (int j = tid; j < k; j += nt) bad |= !(vec1[j] > T(0)) || !(vec1[j] < T(1e30));
+      prev_ok = !__syncthreads_or(bad);
+    }
     // wbar = U diag(1/lam) U^T b   (inverse_matrix + ?gemv + ?symv, eig:37-76, core:651-652)
     const T *b = bvec + u * (int64_t)k;
     for (int j = warp; j < k; j += nw) {
@@ -400,38 +488,40 @@ __global__ void __launch_bounds__(RPL >= 5 ? 256 : 512)
       }
     }
   }
+  __syncthreads();
+  }  // unit loop
 }
 
 template <typename T, int MODE, int RPL>
 static void launch_rpl(cudaStream_t s, int k, int64_t n, T *Cio, const T *b, T *lam, T *wbar, const T *A, T *W,
                        T *V, int32_t *sweeps_max) {
   const int kp = (k + 7) & ~7;
-  const size_t smem_full = sizeof(T) * (3 * (size_t)kp + (size_t)kp * 32 * RPL);
-  const bool smem_ok = smem_full <= 220 * 1024;
+  const size_t smem_full = sizeof(T) * (3 * (size_t)kp + (size_t)kp * (32 * RPL + 4));
+  const bool smem_ok = smem_full <= 216 * 1024;
   LK_REQUIRE(smem_ok || k % 32 == 0,
              "eigensolver: k above the shared-memory limit (160 FP64 / 224 FP32) must be a multiple of 32");
   const size_t smem = smem_ok ? smem_full : sizeof(T) * 3 * (size_t)kp;
   int nwarps = std::max(1, std::min(kp / 8, RPL >= 5 ? 8 : 16));
   const int threads = 32 * nwarps;
-  for (int64_t u0 = 0; u0 < n; u0 += 1 << 30) {
-    const int64_t nu = std::min<int64_t>(n - u0, 1 << 30);
-    const int64_t o2 = u0 * (int64_t)k * k, o1 = u0 * (int64_t)k;
-    if (smem_ok) {
-      auto kern = eig_blk_kernel<T, MODE, RPL, true>;
-      LK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      kern<<<(unsigned)nu, threads, smem, s>>>(k, nu, Cio ? Cio + o2 : nullptr, b ? b + o1 : nullptr,
-                                               lam ? lam + o1 : nullptr, wbar ? wbar + o1 : nullptr,
-                                               A ? A + o2 : nullptr, W ? W + o1 : nullptr, V ? V + o2 : nullptr,
-                                               sweeps_max);
-    } else {
-      auto kern = eig_blk_kernel<T, MODE, RPL, false>;
-      kern<<<(unsigned)nu, threads, smem, s>>>(k, nu, Cio ? Cio + o2 : nullptr, b ? b + o1 : nullptr,
-                                               lam ? lam + o1 : nullptr, wbar ? wbar + o1 : nullptr,
-                                               A ? A + o2 : nullptr, W ? W + o1 : nullptr, V ? V + o2 : nullptr,
-                                               sweeps_max);
-    }
-    launch_counter()++;
+  static const int chain = [] {
+    const char *e = getenv("LETKF_B200_EIG_CHAIN");
+    return e ? atoi(e) : 8;
+  }();
+  // units per CTA: a run of neighbouring grid points solved with warm starts (MODE 0 only)
+  const bool can_chain = MODE == 0 && smem_ok && chain > 1 && kp % 16 == 0 && (kp / 16) * (kp / 16) <= 4 * nwarps;
+  const int run = can_chain ? 8 : 1;
+  const int64_t nblocks = (n + run - 1) / run;
+  LK_REQUIRE(nblocks < ((int64_t)1 << 31), "eigensolver: batch too large for one launch");
+  int32_t *ssum = sweeps_max ? sweeps_max + 1 : nullptr;
+  if (smem_ok) {
+    auto kern = eig_blk_kernel<T, MODE, RPL, true>;
+    LK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<(unsigned)nblocks, threads, smem, s>>>(k, n, run, Cio, b, lam, wbar, A, W, V, sweeps_max, ssum);
+  } else {
+    auto kern = eig_blk_kernel<T, MODE, RPL, false>;
+    kern<<<(unsigned)nblocks, threads, smem, s>>>(k, n, run, Cio, b, lam, wbar, A, W, V, sweeps_max, ssum);
   }
+  launch_counter()++;
   LK_CUDA(cudaGetLastError());
 }
 
