@@ -347,9 +347,9 @@ __device__ __forceinline__ void warp_gemm32_dmma(FA fa, FB fb, double *out, int 
 // tensor pipe (gram32_unit, straight into shared memory), then solves and transforms.  Warps of an SM
 // are at different phases, so Gram work (tensor pipe) of some warps overlaps the Jacobi work (FP64
 // pipe, latency bound) of the others, and C / U never touch global memory.
-template <int RUN, bool GRAM>
+template <bool GRAM>
 __global__ void __launch_bounds__(128, 3)
-    eig32_chain_kernel(int64_t n, double *__restrict__ Cio, const double *__restrict__ bvec,
+    eig32_chain_kernel(int RUN, int64_t n, double *__restrict__ Cio, const double *__restrict__ bvec,
                        double *__restrict__ lam, double *__restrict__ wbar, int32_t *__restrict__ sweeps_max,
                        int32_t *__restrict__ sweeps_sum, bool fused, Xform32Args xa, TreeViews tv, double mu) {
   using T = double;
@@ -475,12 +475,12 @@ void launch_eig32_solve(cudaStream_t s, int64_t n, T *C_inout_U, const T *b, T *
     return e ? atoi(e) : 16;
   }();
   if (chain > 1 && sizeof(T) == 8) {
-    constexpr int RUN = 16;
+    const int RUN = chain;
     const size_t smem = sizeof(double) * 4 * (2 * 32 * LDA32 + 64);
-    auto kern = eig32_chain_kernel<RUN, false>;
+    auto kern = eig32_chain_kernel<false>;
     LK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t nwarp = (n + RUN - 1) / RUN;
-    kern<<<(unsigned)((nwarp + 3) / 4), 128, smem, s>>>(n, reinterpret_cast<double *>(C_inout_U),
+    kern<<<(unsigned)((nwarp + 3) / 4), 128, smem, s>>>(RUN, n, reinterpret_cast<double *>(C_inout_U),
                                                          reinterpret_cast<const double *>(b),
                                                          reinterpret_cast<double *>(lam),
                                                          reinterpret_cast<double *>(wbar), sweeps_max,
@@ -516,12 +516,12 @@ template void launch_eig32_solve<float>(cudaStream_t, int64_t, float *, const fl
 void launch_letkf32_fused(cudaStream_t s, const TreeViews &tv, int64_t n, double mu, const Xform32Args &xa,
                           int32_t *sweeps_max) {
   if (n == 0) return;
-  constexpr int RUN = 16;
+  const int RUN = 16;
   const size_t smem = sizeof(double) * 4 * (2 * 32 * LDA32 + 64);
-  auto kern = eig32_chain_kernel<RUN, true>;
+  auto kern = eig32_chain_kernel<true>;
   LK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t nwarp = (n + RUN - 1) / RUN;
-  kern<<<(unsigned)((nwarp + 3) / 4), 128, smem, s>>>(n, nullptr, nullptr, nullptr, nullptr, sweeps_max,
+  kern<<<(unsigned)((nwarp + 3) / 4), 128, smem, s>>>(RUN, n, nullptr, nullptr, nullptr, nullptr, sweeps_max,
                                                        sweeps_max ? sweeps_max + 1 : nullptr, true, xa, tv, mu);
   launch_counter()++;
   LK_CUDA(cudaGetLastError());
