@@ -365,10 +365,11 @@ def main():
     dom = max(("search", "gram", "eigen", "transform"), key=lambda s_: stage[s_]["ms"])
     roofline = {"kernel": dom, "bound": stage[dom]["bound"], "achieved": stage[dom]["achieved"],
                 "peak": stage[dom]["peak"], "unit": stage[dom]["unit"], "frac": stage[dom]["frac"], "traffic": stage[dom]["traffic_bytes_per_launch"],
-                "traffic_note": "DRAM bytes of one launch (2^18 units) from profiles/ncu_traffic.json; algorithmic "
-                                "(2k^2+k)*8 B = 16.6 KB per eigensolve, measured 17.5 KB",
+                "traffic_note": "DRAM bytes of one launch (2^18 units) from profiles/ncu_traffic.json; the eigen kernel "
+                                "(with the fused transform) reads C, b, xb and writes xa: algorithmic 8.7 KB per unit, "
+                                "measured 8.75 KB",
                 "model": "achieved = 4k^3 flop per eigensolve (SURVEY 8(d) LAPACK model) x units / device time; the "
-                         "Jacobi kernel executes ~7x that, FP64 pipe 40% busy + FP64 tensor pipe 6% (ncu)",
+                         "Jacobi kernel executes ~7x that; ncu: FP64 pipe 42% busy, FP64 tensor pipe 7%, issue 52%",
                 "peak_source": ("letkf_b200_fma_peak micro-benchmark (FP64 FMA, measured in this run)"
                                 if stage[dom]["bound"] == "fp64" else
                                 ("MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s")),
