@@ -136,9 +136,100 @@ struct RoundOp {
   }
 };
 
-// One-sided Jacobi sweeps, register blocked.  G: kp columns (kp multiple of 8, columns >= k are zero)
-// of ld rows (rows >= k are zero / absent; lanes only touch rows < nrows).  nrm: kp values of shared
-// memory.  Returns the number of sweeps.
+// ---- warp-level building blocks of a sweep ---------------------------------------------------------
+// D: column-major data (leading dimension ld) the warp reads / writes; dcol*: first DATA column of a
+// 4-column sub-block in D; ncol*: index of the same sub-block's first column in the norm array (the two
+// differ when D is a staged panel of a larger matrix).
+
+// the 6 pairs inside one sub-block, plus its exact squared column norms
+template <typename T, int RPL, bool FASTROT>
+__device__ __forceinline__ void sub_self(T *D, int ld, int dcol, int ncol, const bool (&rowok)[RPL], T *nrm, int lane,
+                                         T tol2, T stop2, int &rotated, int &big) {
+  T x[4][RPL];
+#pragma unroll
+  for (int c = 0; c < 4; ++c)
+#pragma unroll
+    for (int m = 0; m < RPL; ++m) x[c][m] = rowok[m] ? D[(size_t)(dcol + c) * ld + lane + 32 * m] : T(0);
+  {
+    T sq[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      T a = T(0);
+#pragma unroll
+      for (int m = 0; m < RPL; ++m) a = fma(x[c][m], x[c][m], a);
+      sq[c] = a;
+    }
+    const T nn = reduce4(sq[0], sq[1], sq[2], sq[3], lane);
+    if ((lane & 7) == 0) nrm[ncol + (lane >> 3)] = nn;
+    __syncwarp();
+  }
+  const int h = lane >> 4;  // which of the 2 simultaneous pairs this lane works for
+  // round 0: (0,1) (2,3)   round 1: (0,2) (1,3)   round 2: (0,3) (1,2)
+  RoundOp<T, RPL, 4, 2, FASTROT>::run(
+      x, [](int i) { return 2 * i; }, [](int i) { return 2 * i + 1; }, ncol + 2 * h, ncol + 2 * h + 1, nrm, lane, tol2,
+      stop2, rotated, big);
+  RoundOp<T, RPL, 4, 2, FASTROT>::run(
+      x, [](int i) { return i; }, [](int i) { return i + 2; }, ncol + h, ncol + h + 2, nrm, lane, tol2, stop2, rotated, big);
+  RoundOp<T, RPL, 4, 2, FASTROT>::run(
+      x, [](int i) { return i; }, [](int i) { return 3 - i; }, ncol + h, ncol + 3 - h, nrm, lane, tol2, stop2, rotated, big);
+#pragma unroll
+  for (int c = 0; c < 4; ++c)
+#pragma unroll
+    for (int m = 0; m < RPL; ++m)
+      if (rowok[m]) D[(size_t)(dcol + c) * ld + lane + 32 * m] = x[c][m];
+}
+
+// the 16 cross pairs of two sub-blocks: 4 rounds of 4 disjoint pairs, all from registers
+template <typename T, int RPL, bool FASTROT>
+__device__ __forceinline__ void sub_cross(T *D, int ld, int dcolA, int dcolB, int ncolA, int ncolB,
+                                          const bool (&rowok)[RPL], T *nrm, int lane, T tol2, T stop2, int &rotated,
+                                          int &big) {
+  T x[8][RPL];
+#pragma unroll
+  for (int c = 0; c < 4; ++c)
+#pragma unroll
+    for (int m = 0; m < RPL; ++m) {
+      x[c][m] = rowok[m] ? D[(size_t)(dcolA + c) * ld + lane + 32 * m] : T(0);
+      x[4 + c][m] = rowok[m] ? D[(size_t)(dcolB + c) * ld + lane + 32 * m] : T(0);
+    }
+  const int i = lane >> 3;  // this lane's pair within a round
+  RoundOp<T, RPL, 8, 4, FASTROT>::run(
+      x, [](int i) { return i; }, [](int i) { return 4 + i; }, ncolA + i, ncolB + i, nrm, lane, tol2, stop2, rotated, big);
+  RoundOp<T, RPL, 8, 4, FASTROT>::run(
+      x, [](int i) { return i; }, [](int i) { return 4 + ((i + 1) & 3); }, ncolA + i, ncolB + ((i + 1) & 3), nrm, lane,
+      tol2, stop2, rotated, big);
+  RoundOp<T, RPL, 8, 4, FASTROT>::run(
+      x, [](int i) { return i; }, [](int i) { return 4 + ((i + 2) & 3); }, ncolA + i, ncolB + ((i + 2) & 3), nrm, lane,
+      tol2, stop2, rotated, big);
+  RoundOp<T, RPL, 8, 4, FASTROT>::run(
+      x, [](int i) { return i; }, [](int i) { return 4 + ((i + 3) & 3); }, ncolA + i, ncolB + ((i + 3) & 3), nrm, lane,
+      tol2, stop2, rotated, big);
+#pragma unroll
+  for (int c = 0; c < 4; ++c)
+#pragma unroll
+    for (int m = 0; m < RPL; ++m)
+      if (rowok[m]) {
+        D[(size_t)(dcolA + c) * ld + lane + 32 * m] = x[c][m];
+        D[(size_t)(dcolB + c) * ld + lane + 32 * m] = x[4 + c][m];
+      }
+}
+
+// round-robin partner schedule on nbk (even) items: pair j of step os
+__device__ __forceinline__ void rr_pair(int j, int os, int nbk, int &I, int &J) {
+  const int nm1 = nbk - 1;
+  if (j == 0) {
+    I = nm1;
+    J = os;
+  } else {
+    I = (os + j) % nm1;
+    J = (os - j + nm1) % nm1;
+  }
+}
+
+// One-sided Jacobi sweeps, register blocked, on a matrix that is directly addressable by every warp
+// (shared memory, or global memory for the small generic fallback).  G: kp columns (kp multiple of 8,
+// columns >= k are zero) of ld rows (lanes only touch rows < nrows).  nrm: kp values of shared memory.
+// Returns the number of sweeps.
 template <typename T, int RPL, bool FASTROT>
 __device__ int block_jacobi_rb(T *G, int k, int kp, int ld, int nrows, T *nrm, T stop2) {
   const int tid = threadIdx.x;
@@ -151,84 +242,16 @@ __device__ int block_jacobi_rb(T *G, int k, int kp, int ld, int nrows, T *nrm, T
   int sweeps = 0;
   for (; sweeps < 40; ++sweeps) {
     int rotated = 0, big = 0;
-    // ---- pass 1: pairs inside each block of 4 columns, plus exact column norms ------------------
-    for (int I = warp; I < nb; I += nw) {
-      T x[4][RPL];
-#pragma unroll
-      for (int c = 0; c < 4; ++c)
-#pragma unroll
-        for (int m = 0; m < RPL; ++m) x[c][m] = rowok[m] ? G[(size_t)(4 * I + c) * ld + lane + 32 * m] : T(0);
-      {
-        T sq[4];
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          T a = T(0);
-#pragma unroll
-          for (int m = 0; m < RPL; ++m) a = fma(x[c][m], x[c][m], a);
-          sq[c] = a;
-        }
-        const T nn = reduce4(sq[0], sq[1], sq[2], sq[3], lane);
-        if ((lane & 7) == 0) nrm[4 * I + (lane >> 3)] = nn;
-        __syncwarp();
-      }
-      const int h = lane >> 4;  // which of the 2 simultaneous pairs this lane works for
-      // round 0: (0,1) (2,3)   round 1: (0,2) (1,3)   round 2: (0,3) (1,2)
-      RoundOp<T, RPL, 4, 2, FASTROT>::run(
-          x, [](int i) { return 2 * i; }, [](int i) { return 2 * i + 1; }, 4 * I + 2 * h, 4 * I + 2 * h + 1, nrm, lane,
-          tol2, stop2, rotated, big);
-      RoundOp<T, RPL, 4, 2, FASTROT>::run(
-          x, [](int i) { return i; }, [](int i) { return i + 2; }, 4 * I + h, 4 * I + h + 2, nrm, lane, tol2, stop2,
-          rotated, big);
-      RoundOp<T, RPL, 4, 2, FASTROT>::run(
-          x, [](int i) { return i; }, [](int i) { return 3 - i; }, 4 * I + h, 4 * I + 3 - h, nrm, lane, tol2, stop2,
-          rotated, big);
-#pragma unroll
-      for (int c = 0; c < 4; ++c)
-#pragma unroll
-        for (int m = 0; m < RPL; ++m)
-          if (rowok[m]) G[(size_t)(4 * I + c) * ld + lane + 32 * m] = x[c][m];
-    }
+    // pass 1: pairs inside each block of 4 columns, plus exact column norms
+    for (int I = warp; I < nb; I += nw)
+      sub_self<T, RPL, FASTROT>(G, ld, 4 * I, 4 * I, rowok, nrm, lane, tol2, stop2, rotated, big);
     __syncthreads();
-    // ---- pass 2: all cross pairs of every block pair, round-robin over the blocks ----------------
+    // pass 2: all cross pairs of every block pair, round-robin over the blocks
     for (int os = 0; os < nm1; ++os) {
       for (int j = warp; j < npair; j += nw) {
         int I, J;
-        if (j == 0) {
-          I = nm1;
-          J = os;
-        } else {
-          I = (os + j) % nm1;
-          J = (os - j + nm1) % nm1;
-        }
-        T x[8][RPL];
-#pragma unroll
-        for (int c = 0; c < 4; ++c)
-#pragma unroll
-          for (int m = 0; m < RPL; ++m) {
-            x[c][m] = rowok[m] ? G[(size_t)(4 * I + c) * ld + lane + 32 * m] : T(0);
-            x[4 + c][m] = rowok[m] ? G[(size_t)(4 * J + c) * ld + lane + 32 * m] : T(0);
-          }
-        const int i = lane >> 3;  // this lane's pair within a round
-        RoundOp<T, RPL, 8, 4, FASTROT>::run(
-            x, [](int i) { return i; }, [](int i) { return 4 + i; }, 4 * I + i, 4 * J + i, nrm, lane, tol2, stop2, rotated,
-            big);
-        RoundOp<T, RPL, 8, 4, FASTROT>::run(
-            x, [](int i) { return i; }, [](int i) { return 4 + ((i + 1) & 3); }, 4 * I + i, 4 * J + ((i + 1) & 3), nrm,
-            lane, tol2, stop2, rotated, big);
-        RoundOp<T, RPL, 8, 4, FASTROT>::run(
-            x, [](int i) { return i; }, [](int i) { return 4 + ((i + 2) & 3); }, 4 * I + i, 4 * J + ((i + 2) & 3), nrm,
-            lane, tol2, stop2, rotated, big);
-        RoundOp<T, RPL, 8, 4, FASTROT>::run(
-            x, [](int i) { return i; }, [](int i) { return 4 + ((i + 3) & 3); }, 4 * I + i, 4 * J + ((i + 3) & 3), nrm,
-            lane, tol2, stop2, rotated, big);
-#pragma unroll
-        for (int c = 0; c < 4; ++c)
-#pragma unroll
-          for (int m = 0; m < RPL; ++m)
-            if (rowok[m]) {
-              G[(size_t)(4 * I + c) * ld + lane + 32 * m] = x[c][m];
-              G[(size_t)(4 * J + c) * ld + lane + 32 * m] = x[4 + c][m];
-            }
+        rr_pair(j, os, nb, I, J);
+        sub_cross<T, RPL, FASTROT>(G, ld, 4 * I, 4 * J, 4 * I, 4 * J, rowok, nrm, lane, tol2, stop2, rotated, big);
       }
       __syncthreads();
     }
@@ -293,18 +316,132 @@ __device__ __forceinline__ void block_gemm_dmma(FA fa, FB fb, T *Gout, int ld, i
   __syncthreads();
 }
 
+// Out-of-place variant for matrices with more than 4 output blocks per warp (k % 32 == 0): each warp walks
+// 32 x 32 output blocks (16 DMMA per 8 fragment loads) and stores them straight to Out, which must not
+// alias the operands.
+template <typename T, typename FA, typename FB>
+__device__ __forceinline__ void block_gemm_dmma_oop(FA fa, FB fb, T *Out, int ldo, int kp) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  const int lr = lane >> 2, lc = lane & 3;
+  const int nb32 = kp / 32;
+  __syncthreads();
+  for (int blk = warp; blk < nb32 * nb32; blk += nw) {
+    const int br = 32 * (blk % nb32), bc = 32 * (blk / nb32);
+    double acc[4][4][2];
+#pragma unroll
+    for (int ti = 0; ti < 4; ++ti)
+#pragma unroll
+      for (int tj = 0; tj < 4; ++tj) acc[ti][tj][0] = acc[ti][tj][1] = 0.0;
+#pragma unroll 2
+    for (int kk = 0; kk < kp; kk += 4) {
+      double a[4], b[4];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        a[t] = fa(br + 8 * t + lr, kk + lc);
+        b[t] = fb(kk + lc, bc + 8 * t + lr);
+      }
+#pragma unroll
+      for (int ti = 0; ti < 4; ++ti)
+#pragma unroll
+        for (int tj = 0; tj < 4; ++tj) dmma884b(acc[ti][tj][0], acc[ti][tj][1], a[ti], b[tj]);
+    }
+#pragma unroll
+    for (int ti = 0; ti < 4; ++ti)
+#pragma unroll
+      for (int tj = 0; tj < 4; ++tj) {
+        const int row = br + 8 * ti + lr, col = bc + 8 * tj + 2 * lc;
+        Out[row + (size_t)col * ldo] = (T)acc[ti][tj][0];
+        Out[row + (size_t)(col + 1) * ldo] = (T)acc[ti][tj][1];
+      }
+  }
+  __syncthreads();
+}
+
+// Cholesky of a matrix that lives in global memory / L2 (k % 32 == 0, ld = k, lower triangle valid), blocked
+// left-looking over 32-column panels staged in shared memory (panel: 32 x (k + 4)):
+//   panel = C[c0:k, c0:c0+32] - L[c0:k, 0:c0] L[c0:c0+32, 0:c0]^T   (FP64 tensor pipe, one 32 x 32 block per warp)
+//   factor the panel in shared memory (column by column, as block_cholesky), write its lower part back.
+// The unblocked algorithm on global memory pays an L2 round trip per column update (k^3/3 of them).
+template <typename T>
+__device__ bool block_cholesky_panel(T *G, int k, T *panel) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
+  const int lr = lane >> 2, lc = lane & 3;
+  const int ldp = k + 4;
+  bool ok = true;
+  for (int c0 = 0; c0 < k; c0 += 32) {
+    const int rows = k - c0;
+    __syncthreads();  // earlier panels are in global memory
+    for (int rb = warp; rb < rows / 32; rb += nw) {
+      double acc[4][4][2];
+#pragma unroll
+      for (int ti = 0; ti < 4; ++ti)
+#pragma unroll
+        for (int tj = 0; tj < 4; ++tj) acc[ti][tj][0] = acc[ti][tj][1] = 0.0;
+      const T *Arow = G + c0 + 32 * rb + lr;  // + 8 ti + (kk + lc) k
+      const T *Brow = G + c0 + lr;            // + 8 tj + (kk + lc) k
+#pragma unroll 2
+      for (int kk = 0; kk < c0; kk += 4) {
+        const size_t off = (size_t)(kk + lc) * k;
+        double a[4], b[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          a[t] = (double)Arow[8 * t + off];
+          b[t] = (double)Brow[8 * t + off];
+        }
+#pragma unroll
+        for (int ti = 0; ti < 4; ++ti)
+#pragma unroll
+          for (int tj = 0; tj < 4; ++tj) dmma884b(acc[ti][tj][0], acc[ti][tj][1], a[ti], b[tj]);
+      }
+#pragma unroll
+      for (int ti = 0; ti < 4; ++ti)
+#pragma unroll
+        for (int tj = 0; tj < 4; ++tj) {
+          const int r = 32 * rb + 8 * ti + lr, c = 8 * tj + 2 * lc;
+          panel[r + (size_t)c * ldp] = (T)((double)G[c0 + r + (size_t)(c0 + c) * k] - acc[ti][tj][0]);
+          panel[r + (size_t)(c + 1) * ldp] = (T)((double)G[c0 + r + (size_t)(c0 + c + 1) * k] - acc[ti][tj][1]);
+        }
+    }
+    for (int jj = 0; jj < 32; ++jj) {
+      __syncthreads();
+      const T piv = panel[jj + (size_t)jj * ldp];
+      if (!(piv > T(0))) ok = false;
+      const T d = sqrt(piv);
+      __syncthreads();
+      if (tid == 0) panel[jj + (size_t)jj * ldp] = d;
+      const T dinv = T(1) / d;
+      for (int i = jj + 1 + tid; i < rows; i += nt) panel[i + (size_t)jj * ldp] *= dinv;
+      __syncthreads();
+      for (int c = jj + 1 + warp; c < 32; c += nw) {
+        const T f = panel[c + (size_t)jj * ldp];
+        for (int i = c + lane; i < rows; i += 32) panel[i + (size_t)c * ldp] -= panel[i + (size_t)jj * ldp] * f;
+      }
+    }
+    __syncthreads();
+    for (int e = tid; e < 32 * rows; e += nt) {
+      const int i = e % rows, c = e / rows;
+      if (i >= c) G[c0 + i + (size_t)(c0 + c) * k] = panel[i + (size_t)c * ldp];
+    }
+  }
+  __syncthreads();
+  for (int e = tid; e < k * k; e += nt) {
+    const int i = e % k, j = e / k;
+    if (i < j) G[i + (size_t)j * k] = T(0);
+  }
+  __syncthreads();
+  return ok;
+}
+
 // mode 0: LETKF solve.  in: C (column-major lower triangle, SPD), b.  out: U (column-major, in place of C), lam, wbar.
 // mode 1: ?syevd.      in: A (lower).                  out: W ascending, V.
 template <typename T, int MODE, int RPL, bool SMEM>
 __global__ void __launch_bounds__(RPL >= 5 ? 256 : 512)
     eig_blk_kernel(int k, int64_t n, int run, T *__restrict__ Cio, const T *__restrict__ bvec, T *__restrict__ lam,
                    T *__restrict__ wbar, const T *__restrict__ Ain, T *__restrict__ Wout, T *__restrict__ Vout,
-                   int32_t *__restrict__ sweeps_max, int32_t *__restrict__ sweeps_sum) {
+                   int32_t *__restrict__ sweeps_max, int32_t *__restrict__ sweeps_sum, T *__restrict__ scratch) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T *sm = reinterpret_cast<T *>(smem_raw);
-  const int64_t u0 = (int64_t)blockIdx.x * run;
-  if (u0 >= n) return;
-  const int64_t u1 = u0 + run < n ? u0 + run : n;
   const int tid = threadIdx.x, nt = blockDim.x;
   const int warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
   const int kp = (k + 7) & ~7;
@@ -314,20 +451,27 @@ __global__ void __launch_bounds__(RPL >= 5 ? 256 : 512)
   T *vec1 = sm;             // [kp]
   T *vec2 = sm + kp;        // [kp]
   T *nrm = sm + 2 * kp;     // [kp]
-  T *Gs = sm + 3 * kp;      // [kp * ld] when SMEM
+  T *Gs = sm + 3 * kp;      // [kp * ld] when SMEM, else the 32 x (k + 4) Cholesky panel
   __shared__ T s_shift;
   __shared__ T red_lo[512], red_sc[512];
   // Warm start (MODE 0, shared-memory path, kp % 16 == 0, <= 4 output blocks per warp): the CTA walks
   // `run` consecutive units and solves each in the eigenbasis of the previous one, exactly as the k = 32
   // chained kernel does; U_prev is read back from global memory (L2), the three products run on the
   // FP64 tensor pipe.
-  const bool can_chain = MODE == 0 && SMEM && run > 1 && kp % 16 == 0 && (kp / 16) * (kp / 16) <= 4 * nw;
-  bool prev_ok = false;
+  // Larger matrices (k % 32 == 0, `scratch` given): the same, with out-of-place products through a
+  // k x k scratch matrix per CTA in global memory (L2); the grid is then persistent and strides over runs.
+  const bool chain_small = MODE == 0 && SMEM && run > 1 && kp % 16 == 0 && (kp / 16) * (kp / 16) <= 4 * nw;
+  const bool chain_big = MODE == 0 && !chain_small && run > 1 && scratch != nullptr && k % 32 == 0;
+  const bool can_chain = chain_small || chain_big;
+  T *S = chain_big ? scratch + (size_t)blockIdx.x * k * k : nullptr;
 
   if (SMEM) {
     for (int e = tid; e < kp * ld; e += nt) Gs[e] = T(0);
     __syncthreads();
   }
+  for (int64_t rb = blockIdx.x; rb * run < n; rb += gridDim.x) {
+  const int64_t u0 = rb * run, u1 = u0 + run < n ? u0 + run : n;
+  bool prev_ok = false;
   for (int64_t u = u0; u < u1; ++u) {
   T *Gg = MODE == 0 ? Cio + u * (int64_t)k * k : Vout + u * (int64_t)k * k;
   T *G = SMEM ? Gs : Gg;
@@ -342,14 +486,27 @@ __global__ void __launch_bounds__(RPL >= 5 ? 256 : 512)
       }
     if (tid == 0) s_shift = T(0);
     __syncthreads();
-    if (warm) {
+    if (warm && chain_big) {
+      // S = C U_prev, then C' = U_prev^T S -> G (C: full in shared memory, lower triangle in global)
+      block_gemm_dmma_oop<T>(
+          [&](int i, int l) {
+            return SMEM ? (double)G[i + (size_t)l * ld] : (double)(i >= l ? G[i + (size_t)l * ld] : G[l + (size_t)i * ld]);
+          },
+          [&](int l, int j) { return (double)Up[l + (size_t)j * k]; }, S, k, k);
+      block_gemm_dmma_oop<T>([&](int i, int l) { return (double)Up[l + (size_t)i * k]; },
+                             [&](int l, int j) { return (double)S[l + (size_t)j * k]; }, G, ld, k);
+    } else if (warm) {
       // T = C U_prev, then C' = U_prev^T T (both written over G)
       block_gemm_dmma<T>([&](int i, int l) { return (double)G[i + (size_t)l * ld]; },
                          [&](int l, int j) { return (l < k && j < k) ? (double)Up[l + (size_t)j * k] : 0.0; }, G, ld, kp);
       block_gemm_dmma<T>([&](int i, int l) { return (l < k && i < k) ? (double)Up[l + (size_t)i * k] : 0.0; },
                          [&](int l, int j) { return (double)G[l + (size_t)j * ld]; }, G, ld, kp);
     }
-    block_cholesky(G, k, ld);  // C is SPD by construction; a NaN input propagates
+    // C is SPD by construction; a NaN input propagates
+    if (SMEM)
+      block_cholesky(G, k, ld);
+    else
+      block_cholesky_panel(G, k, Gs);
   } else {
     const T *A = Ain + u * (int64_t)k * k;
     // First try the matrix as it is (an SPD input keeps its full relative accuracy); if a pivot
@@ -388,7 +545,7 @@ __global__ void __launch_bounds__(RPL >= 5 ? 256 : 512)
         for (int i = tid; i < k; i += nt) G[i + (size_t)i * ld] += sh;
         __syncthreads();
       }
-      if (block_cholesky(G, k, ld)) break;
+      if (SMEM ? block_cholesky(G, k, ld) : block_cholesky_panel(G, k, Gs)) break;
     }
   }
 
@@ -412,7 +569,13 @@ __global__ void __launch_bounds__(RPL >= 5 ? 256 : 512)
   __syncthreads();
 
   if (MODE == 0) {
-    if (warm) {
+    if (warm && chain_big) {
+      // U = U_prev U'
+      block_gemm_dmma_oop<T>([&](int i, int l) { return (double)Up[i + (size_t)l * k]; },
+                             [&](int l, int j) { return (double)G[l + (size_t)j * ld]; }, S, k, k);
+      for (int e = tid; e < k * k; e += nt) G[(e % k) + (size_t)(e / k) * ld] = S[e];
+      __syncthreads();
+    } else if (warm) {
       // U = U_prev U'
       block_gemm_dmma<T>([&](int i, int l) { return (i < k && l < k) ? (double)Up[i + (size_t)l * k] : 0.0; },
                          [&](int l, int j) { return (double)G[l + (size_t)j * ld]; }, G, ld, kp);
@@ -490,6 +653,14 @@ __global__ void __launch_bounds__(RPL >= 5 ? 256 : 512)
   }
   __syncthreads();
   }  // unit loop
+  }  // run loop
+}
+
+// warm-start scratch of the persistent large-k kernel: grow-only, lives as long as the library
+static unsigned char *eig_scratch(size_t bytes) {
+  static DevBuf<unsigned char> buf;
+  buf.ensure(bytes);
+  return buf.p;
 }
 
 template <typename T, int MODE, int RPL>
@@ -500,7 +671,7 @@ static void launch_rpl(cudaStream_t s, int k, int64_t n, T *Cio, const T *b, T *
   const bool smem_ok = smem_full <= 216 * 1024;
   LK_REQUIRE(smem_ok || k % 32 == 0,
              "eigensolver: k above the shared-memory limit (160 FP64 / 224 FP32) must be a multiple of 32");
-  const size_t smem = smem_ok ? smem_full : sizeof(T) * 3 * (size_t)kp;
+  const size_t smem = smem_ok ? smem_full : sizeof(T) * (3 * (size_t)kp + 32 * ((size_t)k + 4));  // Cholesky panel
   int nwarps = std::max(1, std::min(kp / 8, RPL >= 5 ? 8 : 16));
   const int threads = 32 * nwarps;
   static const int chain = [] {
@@ -508,19 +679,29 @@ static void launch_rpl(cudaStream_t s, int k, int64_t n, T *Cio, const T *b, T *
     return e ? atoi(e) : 8;
   }();
   // units per CTA: a run of neighbouring grid points solved with warm starts (MODE 0 only)
-  const bool can_chain = MODE == 0 && smem_ok && chain > 1 && kp % 16 == 0 && (kp / 16) * (kp / 16) <= 4 * nwarps;
-  const int run = can_chain ? 8 : 1;
-  const int64_t nblocks = (n + run - 1) / run;
-  LK_REQUIRE(nblocks < ((int64_t)1 << 31), "eigensolver: batch too large for one launch");
+  const bool chain_small = MODE == 0 && smem_ok && chain > 1 && kp % 16 == 0 && (kp / 16) * (kp / 16) <= 4 * nwarps;
+  const bool chain_big = MODE == 0 && !chain_small && chain > 1 && k % 32 == 0;
+  const int run = (chain_small || chain_big) ? 8 : 1;
+  int64_t nblocks = (n + run - 1) / run;
   int32_t *ssum = sweeps_max ? sweeps_max + 1 : nullptr;
-  if (smem_ok) {
-    auto kern = eig_blk_kernel<T, MODE, RPL, true>;
+  auto launch = [&](auto kern) {
     LK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<(unsigned)nblocks, threads, smem, s>>>(k, n, run, Cio, b, lam, wbar, A, W, V, sweeps_max, ssum);
-  } else {
-    auto kern = eig_blk_kernel<T, MODE, RPL, false>;
-    kern<<<(unsigned)nblocks, threads, smem, s>>>(k, n, run, Cio, b, lam, wbar, A, W, V, sweeps_max, ssum);
-  }
+    T *scratch = nullptr;
+    if (chain_big) {  // persistent grid: one k x k scratch matrix per resident CTA
+      int dev = 0, sms = 0, occ = 0;
+      LK_CUDA(cudaGetDevice(&dev));
+      LK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+      LK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
+      nblocks = std::min<int64_t>(nblocks, (int64_t)sms * std::max(occ, 1));
+      scratch = reinterpret_cast<T *>(eig_scratch((size_t)nblocks * k * k * sizeof(T)));
+    }
+    LK_REQUIRE(nblocks < ((int64_t)1 << 31), "eigensolver: batch too large for one launch");
+    kern<<<(unsigned)nblocks, threads, smem, s>>>(k, n, run, Cio, b, lam, wbar, A, W, V, sweeps_max, ssum, scratch);
+  };
+  if (smem_ok)
+    launch(eig_blk_kernel<T, MODE, RPL, true>);
+  else
+    launch(eig_blk_kernel<T, MODE, RPL, false>);
   launch_counter()++;
   LK_CUDA(cudaGetLastError());
 }
