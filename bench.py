@@ -359,17 +359,27 @@ def main():
     except Exception:
         traffic_tab = {}
     per_launch_units = min(units, 1 << 18)
+    tab_k = traffic_tab if a.members == 32 else traffic_tab.get("k%d" % a.members, {})
     for s_ in ("search", "gram", "eigen", "transform"):
-        t_ = traffic_tab.get(s_)
-        stage[s_]["traffic_bytes_per_launch"] = (t_["bytes_per_unit"] * per_launch_units) if (t_ and a.members == 32) else None
+        t_ = tab_k.get(s_)
+        # per launch = per-unit DRAM bytes of the captured launch x the units one launch of this run processes
+        stage[s_]["traffic_bytes_per_launch"] = (t_["bytes_per_unit"] * min(per_launch_units, t_["units_per_launch"])
+                                                 if a.members != 32 else t_["bytes_per_unit"] * per_launch_units) if t_ else None
     dom = max(("search", "gram", "eigen", "transform"), key=lambda s_: stage[s_]["ms"])
     roofline = {"kernel": dom, "bound": stage[dom]["bound"], "achieved": stage[dom]["achieved"],
                 "peak": stage[dom]["peak"], "unit": stage[dom]["unit"], "frac": stage[dom]["frac"], "traffic": stage[dom]["traffic_bytes_per_launch"],
-                "traffic_note": "DRAM bytes of one launch (2^18 units) from profiles/ncu_traffic.json; the eigen kernel "
-                                "(with the fused transform) reads C, b, xb and writes xa: algorithmic 8.7 KB per unit, "
-                                "measured 8.75 KB",
-                "model": "achieved = 4k^3 flop per eigensolve (SURVEY 8(d) LAPACK model) x units / device time; the "
-                         "Jacobi kernel executes ~7x that; ncu: FP64 pipe 42% busy, FP64 tensor pipe 7%, issue 52%",
+                "traffic_note": ("DRAM bytes of one launch (2^18 units) from profiles/ncu_traffic.json; the eigen kernel "
+                                 "(with the fused transform) reads C, b, xb and writes xa: algorithmic 8.7 KB per unit, "
+                                 "measured 8.75 KB") if a.members == 32 else
+                                ("DRAM bytes per launch from profiles/ncu_traffic.json[k%d] if captured; at k = 256 the "
+                                 "matrices live in L2 + shared memory and the warm-start products spill to DRAM "
+                                 "(24.6 MB per unit vs 0.8 MB algorithmic)" % a.members),
+                "model": ("achieved = 4k^3 flop per eigensolve (SURVEY 8(d) LAPACK model) x units / device time; the "
+                          "Jacobi kernel executes ~7x that; ncu: FP64 pipe 42% busy, FP64 tensor pipe 7%, issue 52%")
+                         if a.members == 32 else
+                         ("achieved = 4k^3 flop per eigensolve (SURVEY 8(d) LAPACK model) x units / device time; the "
+                          "block Jacobi kernel executes 4k^3 per sweep (see stages.eigen.mean_sweeps); ncu at k = 256: "
+                          "FP64 pipe 32% busy"),
                 "peak_source": ("letkf_b200_fma_peak micro-benchmark (FP64 FMA, measured in this run)"
                                 if stage[dom]["bound"] == "fp64" else
                                 ("MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s")),

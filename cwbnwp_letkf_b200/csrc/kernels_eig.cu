@@ -137,19 +137,18 @@ struct RoundOp {
 };
 
 // ---- warp-level building blocks of a sweep ---------------------------------------------------------
-// D: column-major data (leading dimension ld) the warp reads / writes; dcol*: first DATA column of a
-// 4-column sub-block in D; ncol*: index of the same sub-block's first column in the norm array (the two
-// differ when D is a staged panel of a larger matrix).
+// P*: first column of a 4-column sub-block (column stride ld*); ncol*: index of that column in the norm
+// array.  The two sub-blocks of a pair may live in different memories (see block_jacobi_rb).
 
 // the 6 pairs inside one sub-block, plus its exact squared column norms
 template <typename T, int RPL, bool FASTROT>
-__device__ __forceinline__ void sub_self(T *D, int ld, int dcol, int ncol, const bool (&rowok)[RPL], T *nrm, int lane,
-                                         T tol2, T stop2, int &rotated, int &big) {
+__device__ __forceinline__ void sub_self(T *P, int ld, int ncol, const bool (&rowok)[RPL], T *nrm, int lane, T tol2,
+                                         T stop2, int &rotated, int &big) {
   T x[4][RPL];
 #pragma unroll
   for (int c = 0; c < 4; ++c)
 #pragma unroll
-    for (int m = 0; m < RPL; ++m) x[c][m] = rowok[m] ? D[(size_t)(dcol + c) * ld + lane + 32 * m] : T(0);
+    for (int m = 0; m < RPL; ++m) x[c][m] = rowok[m] ? P[(size_t)c * ld + lane + 32 * m] : T(0);
   {
     T sq[4];
 #pragma unroll
@@ -176,12 +175,12 @@ __device__ __forceinline__ void sub_self(T *D, int ld, int dcol, int ncol, const
   for (int c = 0; c < 4; ++c)
 #pragma unroll
     for (int m = 0; m < RPL; ++m)
-      if (rowok[m]) D[(size_t)(dcol + c) * ld + lane + 32 * m] = x[c][m];
+      if (rowok[m]) P[(size_t)c * ld + lane + 32 * m] = x[c][m];
 }
 
 // the 16 cross pairs of two sub-blocks: 4 rounds of 4 disjoint pairs, all from registers
 template <typename T, int RPL, bool FASTROT>
-__device__ __forceinline__ void sub_cross(T *D, int ld, int dcolA, int dcolB, int ncolA, int ncolB,
+__device__ __forceinline__ void sub_cross(T *PA, int ldA, T *PB, int ldB, int ncolA, int ncolB,
                                           const bool (&rowok)[RPL], T *nrm, int lane, T tol2, T stop2, int &rotated,
                                           int &big) {
   T x[8][RPL];
@@ -189,8 +188,8 @@ __device__ __forceinline__ void sub_cross(T *D, int ld, int dcolA, int dcolB, in
   for (int c = 0; c < 4; ++c)
 #pragma unroll
     for (int m = 0; m < RPL; ++m) {
-      x[c][m] = rowok[m] ? D[(size_t)(dcolA + c) * ld + lane + 32 * m] : T(0);
-      x[4 + c][m] = rowok[m] ? D[(size_t)(dcolB + c) * ld + lane + 32 * m] : T(0);
+      x[c][m] = rowok[m] ? PA[(size_t)c * ldA + lane + 32 * m] : T(0);
+      x[4 + c][m] = rowok[m] ? PB[(size_t)c * ldB + lane + 32 * m] : T(0);
     }
   const int i = lane >> 3;  // this lane's pair within a round
   RoundOp<T, RPL, 8, 4, FASTROT>::run(
@@ -209,8 +208,8 @@ __device__ __forceinline__ void sub_cross(T *D, int ld, int dcolA, int dcolB, in
 #pragma unroll
     for (int m = 0; m < RPL; ++m)
       if (rowok[m]) {
-        D[(size_t)(dcolA + c) * ld + lane + 32 * m] = x[c][m];
-        D[(size_t)(dcolB + c) * ld + lane + 32 * m] = x[4 + c][m];
+        PA[(size_t)c * ldA + lane + 32 * m] = x[c][m];
+        PB[(size_t)c * ldB + lane + 32 * m] = x[4 + c][m];
       }
 }
 
@@ -226,12 +225,14 @@ __device__ __forceinline__ void rr_pair(int j, int os, int nbk, int &I, int &J) 
   }
 }
 
-// One-sided Jacobi sweeps, register blocked, on a matrix that is directly addressable by every warp
-// (shared memory, or global memory for the small generic fallback).  G: kp columns (kp multiple of 8,
-// columns >= k are zero) of ld rows (lanes only touch rows < nrows).  nrm: kp values of shared memory.
-// Returns the number of sweeps.
+// One-sided Jacobi sweeps, register blocked.  G: kp columns (kp multiple of 8, columns >= k are zero) of ld
+// rows (lanes only touch rows < nrows).  Columns [0, nres) are read and written in R (column stride ldr)
+// instead: the caller keeps as many columns of a matrix that lives in global memory resident in shared
+// memory as fit, which bounds the L2 working set (k = 256 FP64: 148 CTAs x 512 KB thrash the L2 into
+// DRAM otherwise).  nrm: kp values of shared memory.  Returns the number of sweeps.
 template <typename T, int RPL, bool FASTROT>
-__device__ int block_jacobi_rb(T *G, int k, int kp, int ld, int nrows, T *nrm, T stop2) {
+__device__ int block_jacobi_rb(T *G, int k, int kp, int ld, int nrows, T *nrm, T stop2, T *R = nullptr, int ldr = 0,
+                               int nres = 0) {
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31, nw = blockDim.x >> 5;
   const int nb = kp / 4, npair = nb / 2, nm1 = nb - 1;
@@ -239,19 +240,22 @@ __device__ int block_jacobi_rb(T *G, int k, int kp, int ld, int nrows, T *nrm, T
   bool rowok[RPL];
 #pragma unroll
   for (int m = 0; m < RPL; ++m) rowok[m] = lane + 32 * m < nrows;
+  auto colp = [&](int c) { return c < nres ? R + (size_t)c * ldr : G + (size_t)c * ld; };
+  auto cold = [&](int c) { return c < nres ? ldr : ld; };
   int sweeps = 0;
   for (; sweeps < 40; ++sweeps) {
     int rotated = 0, big = 0;
     // pass 1: pairs inside each block of 4 columns, plus exact column norms
     for (int I = warp; I < nb; I += nw)
-      sub_self<T, RPL, FASTROT>(G, ld, 4 * I, 4 * I, rowok, nrm, lane, tol2, stop2, rotated, big);
+      sub_self<T, RPL, FASTROT>(colp(4 * I), cold(4 * I), 4 * I, rowok, nrm, lane, tol2, stop2, rotated, big);
     __syncthreads();
     // pass 2: all cross pairs of every block pair, round-robin over the blocks
     for (int os = 0; os < nm1; ++os) {
       for (int j = warp; j < npair; j += nw) {
         int I, J;
         rr_pair(j, os, nb, I, J);
-        sub_cross<T, RPL, FASTROT>(G, ld, 4 * I, 4 * J, 4 * I, 4 * J, rowok, nrm, lane, tol2, stop2, rotated, big);
+        sub_cross<T, RPL, FASTROT>(colp(4 * I), cold(4 * I), colp(4 * J), cold(4 * J), 4 * I, 4 * J, rowok, nrm, lane,
+                                   tol2, stop2, rotated, big);
       }
       __syncthreads();
     }
@@ -332,7 +336,7 @@ __device__ __forceinline__ void block_gemm_dmma_oop(FA fa, FB fb, T *Out, int ld
     for (int ti = 0; ti < 4; ++ti)
 #pragma unroll
       for (int tj = 0; tj < 4; ++tj) acc[ti][tj][0] = acc[ti][tj][1] = 0.0;
-#pragma unroll 2
+#pragma unroll 4
     for (int kk = 0; kk < kp; kk += 4) {
       double a[4], b[4];
 #pragma unroll
@@ -439,7 +443,8 @@ template <typename T, int MODE, int RPL, bool SMEM>
 __global__ void __launch_bounds__(RPL >= 5 ? 256 : 512)
     eig_blk_kernel(int k, int64_t n, int run, T *__restrict__ Cio, const T *__restrict__ bvec, T *__restrict__ lam,
                    T *__restrict__ wbar, const T *__restrict__ Ain, T *__restrict__ Wout, T *__restrict__ Vout,
-                   int32_t *__restrict__ sweeps_max, int32_t *__restrict__ sweeps_sum, T *__restrict__ scratch) {
+                   int32_t *__restrict__ sweeps_max, int32_t *__restrict__ sweeps_sum, T *__restrict__ scratch,
+                   int nres) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T *sm = reinterpret_cast<T *>(smem_raw);
   const int tid = threadIdx.x, nt = blockDim.x;
@@ -451,7 +456,7 @@ __global__ void __launch_bounds__(RPL >= 5 ? 256 : 512)
   T *vec1 = sm;             // [kp]
   T *vec2 = sm + kp;        // [kp]
   T *nrm = sm + 2 * kp;     // [kp]
-  T *Gs = sm + 3 * kp;      // [kp * ld] when SMEM, else the 32 x (k + 4) Cholesky panel
+  T *Gs = sm + 3 * kp;      // [kp * ld] when SMEM, else the 32 x (k + 4) Cholesky panel / nres resident columns
   __shared__ T s_shift;
   __shared__ T red_lo[512], red_sc[512];
   // Warm start (MODE 0, shared-memory path, kp % 16 == 0, <= 4 output blocks per warp): the CTA walks
@@ -552,7 +557,17 @@ __global__ void __launch_bounds__(RPL >= 5 ? 256 : 512)
   // MODE 0 feeds the LETKF weights (1e-10 bar): stop once a sweep saw only |cos| <= 1e-7 and take the
   // rotation angle in real32.  MODE 1 is the general eigensolver: |cos| <= 1e-9, angle in working precision.
   const T stop2 = MODE == 0 ? T(1e-14) : (sizeof(T) == 8 ? T(1e-18) : T(1e-9));
-  const int sweeps = block_jacobi_rb<T, RPL, MODE == 0>(G, k, kp, ld, k, nrm, stop2);
+  int sweeps;
+  if (SMEM) {
+    sweeps = block_jacobi_rb<T, RPL, MODE == 0>(G, k, kp, ld, k, nrm, stop2);
+  } else {
+    // the first nres columns stay in shared memory for the sweeps (over the Cholesky panel, now free)
+    for (int e = tid; e < nres * k; e += nt) Gs[e] = G[e];
+    __syncthreads();
+    sweeps = block_jacobi_rb<T, RPL, MODE == 0>(G, k, kp, ld, k, nrm, stop2, Gs, k, nres);
+    for (int e = tid; e < nres * k; e += nt) G[e] = Gs[e];
+    __syncthreads();
+  }
   if (tid == 0 && sweeps_max) atomicMax(sweeps_max, sweeps);
   if (tid == 0 && sweeps_sum) atomicAdd(sweeps_sum, sweeps);
 
@@ -671,7 +686,12 @@ static void launch_rpl(cudaStream_t s, int k, int64_t n, T *Cio, const T *b, T *
   const bool smem_ok = smem_full <= 216 * 1024;
   LK_REQUIRE(smem_ok || k % 32 == 0,
              "eigensolver: k above the shared-memory limit (160 FP64 / 224 FP32) must be a multiple of 32");
-  const size_t smem = smem_ok ? smem_full : sizeof(T) * (3 * (size_t)kp + 32 * ((size_t)k + 4));  // Cholesky panel
+  // in-global variant: Cholesky panel, then (FP64) as many resident columns as fit beside ~10 KB of static
+  // arrays.  FP32 matrices (256 KB at k = 256) stay in L2 and run two CTAs per SM instead.
+  const int nres =
+      (smem_ok || sizeof(T) == 4) ? 0 : std::min(k, (int)((216 * 1024 - sizeof(T) * 3 * kp) / (sizeof(T) * k)) & ~3);
+  const size_t smem = smem_ok ? smem_full
+                              : sizeof(T) * (3 * (size_t)kp + std::max(32 * ((size_t)k + 4), (size_t)nres * k));
   int nwarps = std::max(1, std::min(kp / 8, RPL >= 5 ? 8 : 16));
   const int threads = 32 * nwarps;
   static const int chain = [] {
@@ -681,7 +701,7 @@ static void launch_rpl(cudaStream_t s, int k, int64_t n, T *Cio, const T *b, T *
   // units per CTA: a run of neighbouring grid points solved with warm starts (MODE 0 only)
   const bool chain_small = MODE == 0 && smem_ok && chain > 1 && kp % 16 == 0 && (kp / 16) * (kp / 16) <= 4 * nwarps;
   const bool chain_big = MODE == 0 && !chain_small && chain > 1 && k % 32 == 0;
-  const int run = (chain_small || chain_big) ? 8 : 1;
+  const int run = chain_big ? 16 : chain_small ? 8 : 1;
   int64_t nblocks = (n + run - 1) / run;
   int32_t *ssum = sweeps_max ? sweeps_max + 1 : nullptr;
   auto launch = [&](auto kern) {
@@ -696,7 +716,8 @@ static void launch_rpl(cudaStream_t s, int k, int64_t n, T *Cio, const T *b, T *
       scratch = reinterpret_cast<T *>(eig_scratch((size_t)nblocks * k * k * sizeof(T)));
     }
     LK_REQUIRE(nblocks < ((int64_t)1 << 31), "eigensolver: batch too large for one launch");
-    kern<<<(unsigned)nblocks, threads, smem, s>>>(k, n, run, Cio, b, lam, wbar, A, W, V, sweeps_max, ssum, scratch);
+    kern<<<(unsigned)nblocks, threads, smem, s>>>(k, n, run, Cio, b, lam, wbar, A, W, V, sweeps_max, ssum, scratch,
+                                                  nres);
   };
   if (smem_ok)
     launch(eig_blk_kernel<T, MODE, RPL, true>);

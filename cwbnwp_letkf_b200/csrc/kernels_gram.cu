@@ -402,8 +402,11 @@ struct RowMeta2 {
   int pass;
 };
 
-template <typename T>
-__global__ void __launch_bounds__(256)
+// NS = 32 x 32 super-blocks per warp.  One per warp keeps every SM sub-partition busy (k = 256: 12 warps per
+// CTA, 3 per sub-partition; two left 6 of 8 warps active and was 1.7x slower); two per warp (168 registers,
+// hence the smaller block) halves the barriers per DMMA where the blocks split evenly (k = 96, 128).
+template <typename T, int NS>
+__global__ void __launch_bounds__(NS == 2 ? 256 : 512)
     gram_tma_kernel(TreeViews tv, int k, int S, int sb_per_cta, int64_t nunits, const int32_t *__restrict__ unit_pt,
                     double mu, T *__restrict__ C, T *__restrict__ bvec, int32_t *__restrict__ nanflag) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -429,12 +432,12 @@ __global__ void __launch_bounds__(256)
     mbar_init(&bars[1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  int sbi[2], sbj[2];
-  bool has[2];
+  int sbi[NS], sbj[NS];
+  bool has[NS];
 #pragma unroll
-  for (int s = 0; s < 2; ++s) {
-    const int lin = blockIdx.y * sb_per_cta + warp * 2 + s;
-    has[s] = (warp * 2 + s) < sb_per_cta && lin < NSB;
+  for (int s = 0; s < NS; ++s) {
+    const int lin = blockIdx.y * sb_per_cta + warp * NS + s;
+    has[s] = (warp * NS + s) < sb_per_cta && lin < NSB;
     int i = 0, rem = has[s] ? lin : 0;
     while (rem > i) {
       rem -= i + 1;
@@ -443,9 +446,9 @@ __global__ void __launch_bounds__(256)
     sbi[s] = i;
     sbj[s] = rem;
   }
-  double acc[2][16][2];
+  double acc[NS][16][2];
 #pragma unroll
-  for (int s = 0; s < 2; ++s)
+  for (int s = 0; s < NS; ++s)
 #pragma unroll
     for (int t = 0; t < 16; ++t) acc[s][t][0] = acc[s][t][1] = 0.0;
   double bacc = 0.0;
@@ -527,7 +530,7 @@ __global__ void __launch_bounds__(256)
       }
     }
 #pragma unroll
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < NS; ++s) {
       if (!has[s]) continue;
       const bool diag = sbi[s] == sbj[s];
 #pragma unroll 2
@@ -568,7 +571,7 @@ __global__ void __launch_bounds__(256)
   }
   T *Cu = C + unit * (int64_t)k * k;
 #pragma unroll
-  for (int s = 0; s < 2; ++s) {
+  for (int s = 0; s < NS; ++s) {
     if (!has[s]) continue;
     const bool diag = sbi[s] == sbj[s];
 #pragma unroll
@@ -603,13 +606,21 @@ void launch_gram_tma(cudaStream_t s, const TreeViews &tv, int k, int64_t nunits,
   const int NSB = S * (S + 1) / 2;
   const int ncta = (NSB + 15) / 16;
   const int sb_per_cta = (NSB + ncta - 1) / ncta;
-  int nwarps = (sb_per_cta + 1) / 2;
+  // two super-blocks per warp when that splits evenly (k = 96, 128: fewer barriers per DMMA), else one
+  const bool two = sb_per_cta % 2 == 0 && sb_per_cta <= 10;
+  const int ns = two ? 2 : 1;
+  int nwarps = (sb_per_cta + ns - 1) / ns;
   nwarps = std::max(nwarps, (k + 31) / 32);
   const size_t smem = (size_t)2 * kRows * (4 * k + 32) + 2 * kRows * sizeof(RowMeta2);
-  auto kern = gram_tma_kernel<T>;
-  LK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<dim3((unsigned)nunits, (unsigned)ncta), 32 * nwarps, smem, s>>>(tv, k, S, sb_per_cta, nunits, unit_pt,
-                                                                          (double)mu, C, b, nanflag);
+  auto launch = [&](auto kern) {
+    LK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<dim3((unsigned)nunits, (unsigned)ncta), 32 * nwarps, smem, s>>>(tv, k, S, sb_per_cta, nunits, unit_pt,
+                                                                            (double)mu, C, b, nanflag);
+  };
+  if (two)
+    launch(gram_tma_kernel<T, 2>);
+  else
+    launch(gram_tma_kernel<T, 1>);
   launch_counter()++;
   LK_CUDA(cudaGetLastError());
 }
