@@ -361,9 +361,9 @@ template void launch_gram_dmma<float>(cudaStream_t, const TreeViews &, int, int6
 
 // =====================================================================================================
 // TMA-staged variant of the tensor-core Gram (k % 4 == 0).  The rows of a batch are 4k-byte contiguous
-// lines of the ob-major perturbation table; one elected thread gathers them with 1-D bulk asynchronous
-// copies (cp.async.bulk.shared.global, completion on an mbarrier) into a double-buffered shared-memory
-// stage, so the gather of batch i+1 is in flight while batch i feeds the tensor pipe.  Rows are kept as
+// lines of the ob-major perturbation table; a producer warp gathers them with 1-D bulk asynchronous
+// copies (cp.async.bulk.shared.global, completion on an mbarrier) into a ring of shared-memory stages,
+// so the gathers of the next batches are in flight while the current one feeds the tensor pipe.  Rows are kept as
 // the raw real32 perturbations (row stride 4k+32 bytes: the 4 rows of an MMA fragment fall in distinct
 // bank groups); yb = pert*error_inv (single real32 rounding) and the promotion to double happen in
 // registers when a fragment is loaded, so there is no separate conversion pass.
@@ -402,36 +402,101 @@ struct RowMeta2 {
   int pass;
 };
 
-// NS = 32 x 32 super-blocks per warp.  One per warp keeps every SM sub-partition busy (k = 256: 12 warps per
-// CTA, 3 per sub-partition; two left 6 of 8 warps active and was 1.7x slower); two per warp (168 registers,
-// hence the smaller block) halves the barriers per DMMA where the blocks split evenly (k = 96, 128).
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+constexpr int kStages = 3;
+
+// Warp-specialised: the LAST warp of the CTA is the producer.  Per batch of kRows candidate rows it
+// evaluates the row metadata (QC verdict, localised 1/error, scaled departure), publishes it in shared
+// memory, and gathers the passing rows with bulk asynchronous copies that complete on the stage's `full`
+// mbarrier.  The other warps are consumers: wait for `full`, feed the tensor pipe from the stage, arrive on
+// the stage's `empty` mbarrier.  No CTA-wide barrier inside the loop, kStages batches in flight.
+// NS = 32 x 32 super-blocks per consumer warp.  One per warp keeps every SM sub-partition busy (k = 256: 12
+// warps, 3 per sub-partition; two left 6 of 8 warps active and was 1.7x slower); two per warp (168
+// registers, hence the smaller block) where the blocks split evenly (k = 96, 128).
 template <typename T, int NS>
-__global__ void __launch_bounds__(NS == 2 ? 256 : 512)
+__global__ void __launch_bounds__(NS == 2 ? 288 : 512)
     gram_tma_kernel(TreeViews tv, int k, int S, int sb_per_cta, int64_t nunits, const int32_t *__restrict__ unit_pt,
                     double mu, T *__restrict__ C, T *__restrict__ bvec, int32_t *__restrict__ nanflag) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int rowb = 4 * k + 32;  // bytes per staged row
-  unsigned char *stage0 = smem_raw;
-  unsigned char *stage1 = smem_raw + (size_t)kRows * rowb;
-  RowMeta2 *meta = reinterpret_cast<RowMeta2 *>(smem_raw + (size_t)2 * kRows * rowb);  // [2][kRows]
-  __shared__ __align__(8) uint64_t bars[2];
+  RowMeta2 *meta = reinterpret_cast<RowMeta2 *>(smem_raw + (size_t)kStages * kRows * rowb);  // [kStages][kRows]
+  __shared__ __align__(8) uint64_t full[kStages], empty[kStages];
   __shared__ int s_nan;
-  __shared__ unsigned s_pmask[2];
-  __shared__ int s_more[2];
+  __shared__ unsigned s_pmask[kStages];
+  __shared__ int s_last[kStages];
 
   const int64_t unit = blockIdx.x;
   if (unit >= nunits) return;
   const int64_t q = unit_pt[unit];
-  const int tid = threadIdx.x, nt = blockDim.x;
+  const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
+  const int nc = (blockDim.x >> 5) - 1;  // consumer warps
   const int lr = lane >> 2, lc = lane & 3;
   const int NSB = S * (S + 1) / 2;
   if (tid == 0) {
     s_nan = 0;
-    mbar_init(&bars[0], 1);
-    mbar_init(&bars[1], 1);
+    for (int st = 0; st < kStages; ++st) {
+      mbar_init(&full[st], 1);
+      mbar_init(&empty[st], nc);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  __syncthreads();
+
+  if (warp == nc) {
+    // ---------------------------------------- producer ---------------------------------------------
+    int it_t = 0, it_c0 = 0;  // tree index and candidate offset of the current batch
+    auto advance_to_valid = [&]() {  // skip exhausted / empty trees
+      while (it_t < tv.ntrees && it_c0 >= tv.t[it_t].cnt[q] * tv.t[it_t].nact) {
+        ++it_t;
+        it_c0 = 0;
+      }
+    };
+    advance_to_valid();
+    for (int bt = 0;; ++bt) {
+      const int slot = bt % kStages;
+      if (bt >= kStages) mbar_wait(&empty[slot], (uint32_t)((bt / kStages - 1) & 1));
+      RowMeta2 m{0.f, 0.f, 0};
+      const float *src = nullptr;
+      bool last = true;
+      if (it_t < tv.ntrees) {
+        const TreeView &TV = tv.t[it_t];
+        const int ncand = TV.cnt[q] * TV.nact;
+        const int c = it_c0 + lane;
+        if (c < ncand) {
+          const int j = c / TV.nact, a = c - j * TV.nact;
+          const int64_t o = (int64_t)(TV.idx[q * TV.nalloc + j] - 1) * TV.nvar + TV.act[a];
+          if (TV.pass[o]) {
+            m.pass = 1;
+            m.ei = lk_error_inv(TV.err[o], TV.r2[q * TV.nalloc + j], tv.weight_function);
+            m.yo = LK_MUL(TV.omm[o], m.ei);
+            src = TV.pert + o * k;
+            if (m.ei != m.ei) s_nan = 1;
+          }
+        }
+        it_c0 += kRows;
+        advance_to_valid();
+        last = it_t >= tv.ntrees;
+      }
+      meta[slot * kRows + lane] = m;
+      const unsigned pm = __ballot_sync(0xffffffffu, m.pass != 0);
+      if (lane == 0) {
+        s_pmask[slot] = pm;
+        s_last[slot] = last ? 1 : 0;
+      }
+      __syncwarp();  // metadata of all lanes ordered before the (releasing) arrive of lane 0
+      if (lane == 0) mbar_expect_tx(&full[slot], (uint32_t)(__popc(pm) * 4 * k));
+      __syncwarp();
+      if (m.pass) tma_bulk_g2s(smem_raw + ((size_t)slot * kRows + lane) * rowb, src, (uint32_t)(4 * k), &full[slot]);
+      if (last) break;
+    }
+    return;
+  }
+
+  // ------------------------------------------ consumers ----------------------------------------------
   int sbi[NS], sbj[NS];
   bool has[NS];
 #pragma unroll
@@ -452,74 +517,13 @@ __global__ void __launch_bounds__(NS == 2 ? 256 : 512)
 #pragma unroll
     for (int t = 0; t < 16; ++t) acc[s][t][0] = acc[s][t][1] = 0.0;
   double bacc = 0.0;
-  __syncthreads();
 
-  // batch iterator state (identical in every thread): tree index and candidate offset
-  int it_t = 0, it_c0 = 0;
-  auto advance_to_valid = [&]() {  // skip exhausted / empty trees
-    while (it_t < tv.ntrees && it_c0 >= tv.t[it_t].cnt[q] * tv.t[it_t].nact) {
-      ++it_t;
-      it_c0 = 0;
-    }
-  };
-  // warp 0 prepares batch `slot`: row metadata + the bulk copies of its passing rows
-  auto produce = [&](int slot) {
-    if (warp != 0) return;
-    const TreeView &TV = tv.t[it_t];
-    const int ncand = TV.cnt[q] * TV.nact;
-    RowMeta2 m{0.f, 0.f, 0};
-    const float *src = nullptr;
-    const int c = it_c0 + lane;
-    if (c < ncand) {
-      const int j = c / TV.nact, a = c - j * TV.nact;
-      const int64_t o = (int64_t)(TV.idx[q * TV.nalloc + j] - 1) * TV.nvar + TV.act[a];
-      if (TV.pass[o]) {
-        m.pass = 1;
-        m.ei = lk_error_inv(TV.err[o], TV.r2[q * TV.nalloc + j], tv.weight_function);
-        m.yo = LK_MUL(TV.omm[o], m.ei);
-        src = TV.pert + o * k;
-        if (m.ei != m.ei) s_nan = 1;
-      }
-    }
-    meta[slot * kRows + lane] = m;
-    const unsigned pm = __ballot_sync(0xffffffffu, m.pass != 0);
-    if (lane == 0) {
-      s_pmask[slot] = pm;
-      mbar_expect_tx(&bars[slot], (uint32_t)(__popc(pm) * 4 * k));
-    }
-    __syncwarp();
-    if (m.pass) tma_bulk_g2s((slot ? stage1 : stage0) + (size_t)lane * rowb, src, (uint32_t)(4 * k), &bars[slot]);
-  };
-
-  advance_to_valid();
-  bool more = it_t < tv.ntrees;
-  if (more) produce(0);
-  int slot = 0;
-  uint32_t phase[2] = {0u, 0u};
-  while (more) {
-    // position of the NEXT batch
-    int nt_t = it_t, nt_c0 = it_c0 + kRows;
-    {
-      const int sv_t = it_t, sv_c0 = it_c0;
-      it_t = nt_t;
-      it_c0 = nt_c0;
-      advance_to_valid();
-      nt_t = it_t;
-      nt_c0 = it_c0;
-      it_t = sv_t;
-      it_c0 = sv_c0;
-    }
-    const bool next_more = nt_t < tv.ntrees;
-    if (next_more) {  // prefetch the next batch into the other stage (its previous contents were consumed
-      it_t = nt_t;    // before the __syncthreads at the end of the previous iteration)
-      it_c0 = nt_c0;
-      produce(slot ^ 1);
-    }
-    __syncthreads();  // metadata of `slot` visible to all
-    mbar_wait(&bars[slot], phase[slot]);
-    phase[slot] ^= 1u;
+  for (int bt = 0;; ++bt) {
+    const int slot = bt % kStages;
+    mbar_wait(&full[slot], (uint32_t)((bt / kStages) & 1));
     const unsigned pmask = s_pmask[slot];
-    const unsigned char *st = slot ? stage1 : stage0;
+    const bool last = s_last[slot] != 0;
+    const unsigned char *st = smem_raw + (size_t)slot * kRows * rowb;
     const RowMeta2 *mt = meta + slot * kRows;
     if (blockIdx.y == 0 && tid < k) {
 #pragma unroll 4
@@ -565,9 +569,9 @@ __global__ void __launch_bounds__(NS == 2 ? 256 : 512)
           }
       }
     }
-    __syncthreads();  // stage `slot` fully consumed: it may be refilled by the next produce()
-    more = next_more;
-    slot ^= 1;
+    __syncwarp();  // every lane has read the stage before lane 0 hands it back
+    if (lane == 0) mbar_arrive(&empty[slot]);
+    if (last) break;
   }
   T *Cu = C + unit * (int64_t)k * k;
 #pragma unroll
@@ -611,10 +615,12 @@ void launch_gram_tma(cudaStream_t s, const TreeViews &tv, int k, int64_t nunits,
   const int ns = two ? 2 : 1;
   int nwarps = (sb_per_cta + ns - 1) / ns;
   nwarps = std::max(nwarps, (k + 31) / 32);
-  const size_t smem = (size_t)2 * kRows * (4 * k + 32) + 2 * kRows * sizeof(RowMeta2);
+  const size_t smem = (size_t)kStages * kRows * (4 * k + 32) + kStages * kRows * sizeof(RowMeta2);
   auto launch = [&](auto kern) {
     LK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<dim3((unsigned)nunits, (unsigned)ncta), 32 * nwarps, smem, s>>>(tv, k, S, sb_per_cta, nunits, unit_pt,
+    // + 1: the producer warp (k <= 256: at most 15 consumer warps)
+    LK_REQUIRE(nwarps + 1 <= (two ? 9 : 16), "launch_gram_tma: too many warps");
+    kern<<<dim3((unsigned)nunits, (unsigned)ncta), 32 * (nwarps + 1), smem, s>>>(tv, k, S, sb_per_cta, nunits, unit_pt,
                                                                             (double)mu, C, b, nanflag);
   };
   if (two)
