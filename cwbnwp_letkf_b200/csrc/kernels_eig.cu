@@ -230,7 +230,7 @@ __device__ __forceinline__ void rr_pair(int j, int os, int nbk, int &I, int &J) 
 // instead: the caller keeps as many columns of a matrix that lives in global memory resident in shared
 // memory as fit, which bounds the L2 working set (k = 256 FP64: 148 CTAs x 512 KB thrash the L2 into
 // DRAM otherwise).  nrm: kp values of shared memory.  Returns the number of sweeps.
-template <typename T, int RPL, bool FASTROT>
+template <typename T, int RPL, bool FASTROT, bool MIXED = false>
 __device__ int block_jacobi_rb(T *G, int k, int kp, int ld, int nrows, T *nrm, T stop2, T *R = nullptr, int ldr = 0,
                                int nres = 0) {
   const int tid = threadIdx.x;
@@ -240,8 +240,9 @@ __device__ int block_jacobi_rb(T *G, int k, int kp, int ld, int nrows, T *nrm, T
   bool rowok[RPL];
 #pragma unroll
   for (int m = 0; m < RPL; ++m) rowok[m] = lane + 32 * m < nrows;
-  auto colp = [&](int c) { return c < nres ? R + (size_t)c * ldr : G + (size_t)c * ld; };
-  auto cold = [&](int c) { return c < nres ? ldr : ld; };
+  // (MIXED is a template flag so that the all-shared-memory instantiation keeps plain LDS / STS addressing)
+  auto colp = [&](int c) { return (MIXED && c < nres) ? R + (size_t)c * ldr : G + (size_t)c * ld; };
+  auto cold = [&](int c) { return (MIXED && c < nres) ? ldr : ld; };
   int sweeps = 0;
   for (; sweeps < 40; ++sweeps) {
     int rotated = 0, big = 0;
@@ -564,7 +565,7 @@ __global__ void __launch_bounds__(RPL >= 5 ? 256 : 512)
     // the first nres columns stay in shared memory for the sweeps (over the Cholesky panel, now free)
     for (int e = tid; e < nres * k; e += nt) Gs[e] = G[e];
     __syncthreads();
-    sweeps = block_jacobi_rb<T, RPL, MODE == 0>(G, k, kp, ld, k, nrm, stop2, Gs, k, nres);
+    sweeps = block_jacobi_rb<T, RPL, MODE == 0, true>(G, k, kp, ld, k, nrm, stop2, Gs, k, nres);
     for (int e = tid; e < nres * k; e += nt) G[e] = Gs[e];
     __syncthreads();
   }

@@ -122,6 +122,8 @@ def _ptr(a):
 class LetkfB200:
     """One GPU's local-analysis engine (one per process / rank, like one MPI rank of the reference)."""
 
+    fuses_tune_q = True   # analyze() applies letkf_tune_q itself when cfg.tune_q is set (driver.py)
+
     def __init__(self, nmember: int, real64: bool = True, device: int = 0):
         self.L = load_library()
         self.k, self.real64, self.device = int(nmember), bool(real64), int(device)

@@ -79,3 +79,24 @@ def allgather_members(local, k: int, rank: int, world: int):
     for r in range(world):
         parts[r].copy_(bufs[r][: parts[r].shape[0]])
     return full
+
+
+def _block_cyclic(start: int, n: int, nproc: int, nb: int) -> np.ndarray:
+    """0-based indices 'do i = start, n, stride; do j = i, min(n, i+nb-1)' (module_mpi_util.f90:84-103)
+    with start = id*nb + 1, stride = nproc*nb."""
+    out = []
+    i = start * nb + 1
+    while i <= n:
+        out.extend(range(i, min(n, i + nb - 1) + 1))
+        i += nproc * nb
+    return np.asarray(out, np.int64) - 1
+
+
+def local_index_tables(rank: int, world: int, nx: int, ny: int, nxb: int = 1, nyb: int = 1) -> dict:
+    """The four index tables of letkf_local_info (module_mpi_util.f90:73-172), 0-based: mass columns
+    ``xloc``/``yloc`` and the staggered ``xloc_u`` (over nx+1) / ``yloc_v`` (over ny+1).  Block-cyclic
+    with block sizes nxb, nyb (1 in the shipped namelist)."""
+    npx, npy = process_grid(world)
+    idx, idy = rank % npx, rank // npx
+    return {"xloc": _block_cyclic(idx, nx, npx, nxb), "yloc": _block_cyclic(idy, ny, npy, nyb),
+            "xloc_u": _block_cyclic(idx, nx + 1, npx, nxb), "yloc_v": _block_cyclic(idy, ny + 1, npy, nyb)}

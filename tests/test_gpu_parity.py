@@ -389,3 +389,28 @@ def test_syevd_batched_against_lapack(k, dtype):
                     # error grows like sqrt(k*sweeps)*eps (LAPACK's tridiagonal path touches each
                     # entry ~k times).  Measured <= 3e-5 at k=256; bound stated with margin.
                     assert _relerr(f_gpu, f_true) < 1e-6 * max(k, 16)
+
+
+# ------------------------------------------------------------------------------ letkf_driver mirror
+def test_driver_all_variables_match_oracle_driver():
+    """The per-variable dispatch (stagger rules, coordinate caching, tune_q, per-column weight sharing for
+    2-D localised variables) through the C ABI == the same dispatch through the CPU oracle."""
+    from cwbnwp_letkf_b200 import driver as D
+    from _driver_case import OracleBackend, VARS, copy_state, make_state, namelist
+    sc, wrf, proj = make_state()
+    ref = copy_state(wrf)
+    D.LetkfDriver(OracleBackend(sc), namelist, proj).run(ref, VARS)
+    eng = H.LetkfB200(sc.k)
+    for o in sc.obs.values():
+        eng.set_obs(o)
+    got = copy_state(wrf)
+    log = D.LetkfDriver(eng, namelist, proj).run(got, VARS)
+    assert [n for n, _ in log] == VARS
+    for key in ("u", "v", "w", "t", "qv", "qr", "p", "mu", "ph"):
+        a, b = got[key], ref[key]
+        assert np.array_equal(np.isnan(a), np.isnan(b)), key
+        ok = ~np.isnan(b)
+        scale = np.abs(b[ok]).max()
+        assert np.abs(a[ok] - b[ok]).max() <= 5e-7 * scale, key
+        untouched = (b == wrf[key]) | np.isnan(b)
+        assert np.array_equal(a[untouched & ok], wrf[key][untouched & ok]), key
