@@ -50,6 +50,10 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--nxb", type=int, default=16,
+                    help="block size along x of the block-cyclic column decomposition (the reference's nxb, "
+                         "module_mpi_util.f90:10; results do not depend on it)")
+    ap.add_argument("--nyb", type=int, default=1)
     return ap.parse_args()
 
 
@@ -155,7 +159,9 @@ def main():
     config = {"workload": workload, "members": a.members, "variable": a.var,
               "namelist": "input.nml (hclr/vclr/max_lz_pts/inflation/RTPP/RTPS as shipped)",
               "l2": "inputs larger than L2 (ensemble field %.2f GB)" % (a.nx * a.ny * a.nz * a.members * 4 / 1e9),
-              "partition": "1 GPU" if world == 1 else f"columns cyclic over {world} ranks, obs replicated"}
+              "partition": "1 GPU" if world == 1 else
+              "columns block-cyclic (nxb=%d, nyb=%d) over a %dx%d process grid, obs replicated" %
+              ((a.nxb, a.nyb) + P.process_grid(world))}
 
     if a.impl == "reference":
         if rank != 0:
@@ -222,7 +228,7 @@ def main():
     t_obs = time.perf_counter() - t_obs0
 
     # ---- this rank's columns (2-D cyclic process grid, module_mpi_util.f90:80-127) ----
-    pts = P.local_points(rank, world, sc.nx, sc.ny, sc.nz)
+    pts = P.local_points(rank, world, sc.nx, sc.ny, sc.nz, a.nxb, a.nyb)
     xyz_local = np.ascontiguousarray(sc.xyz_grid[pts]) if world > 1 else sc.xyz_grid
     npts_local = xyz_local.shape[0]
     total_pts = sc.npts

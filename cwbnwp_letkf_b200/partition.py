@@ -29,19 +29,19 @@ def process_grid(world: int) -> Tuple[int, int]:
     return best
 
 
-def local_columns(rank: int, world: int, nx: int, ny: int) -> np.ndarray:
-    """Flattened (i + nx*j) indices of the columns rank owns, i fastest (module_mpi_util.f90:80-127)."""
-    npx, npy = process_grid(world)
-    idx, idy = rank % npx, rank // npx
-    xs = np.arange(idx, nx, npx)
-    ys = np.arange(idy, ny, npy)
-    return (xs[None, :] + nx * ys[:, None]).reshape(-1)
+def local_columns(rank: int, world: int, nx: int, ny: int, nxb: int = 1, nyb: int = 1) -> np.ndarray:
+    """Flattened (i + nx*j) indices of the columns rank owns, i fastest (module_mpi_util.f90:80-127).
+    nxb / nyb are the reference's block sizes (compile-time parameters, 1 as shipped, mpi:10-11).  Results
+    do not depend on them; a block of 16 along x keeps the eigensolver's warm-start runs on truly adjacent
+    columns when the grid is split along x."""
+    t = local_index_tables(rank, world, nx, ny, nxb, nyb)
+    return (t["xloc"][None, :] + nx * t["yloc"][:, None]).reshape(-1)
 
 
-def local_points(rank: int, world: int, nx: int, ny: int, nz: int) -> np.ndarray:
+def local_points(rank: int, world: int, nx: int, ny: int, nz: int, nxb: int = 1, nyb: int = 1) -> np.ndarray:
     """Global point indices (i + nx*(j + ny*l)) of the rank's slab, local order i, j, then level --
     the memory order of var(loc_nx, loc_ny, nz, :) (module_letkf_core.f90:85)."""
-    cols = local_columns(rank, world, nx, ny)
+    cols = local_columns(rank, world, nx, ny, nxb, nyb)
     return (cols[None, :] + nx * ny * np.arange(nz)[:, None]).reshape(-1)
 
 

@@ -414,3 +414,112 @@ def test_driver_all_variables_match_oracle_driver():
         assert np.abs(a[ok] - b[ok]).max() <= 5e-7 * scale, key
         untouched = (b == wrf[key]) | np.isnan(b)
         assert np.array_equal(a[untouched & ok], wrf[key][untouched & ok]), key
+
+
+# ------------------------------------------------------------------------------ more member counts
+@pytest.mark.parametrize("k", [64, 128, 160, 192, 256])
+def test_weights_large_member_counts_variable_T(k):
+    """k = 64 / 128: shared-memory block Jacobi with the in-register warm-start chain; 160: shared memory +
+    out-of-place chain; 192 / 256: matrix in global memory (panel Cholesky, resident columns, chain).
+    Variable T gives p > k rows at most points."""
+    sc, _ = S.scenario_tiny(k=k, nx=8, ny=5, nz=4)
+    _weights_case(sc, C.sample_namelist("T"), True, TOL64, npick=10)
+
+
+# ------------------------------------------------------------------------------ edge cases
+def _field_parity(sc, cfg, f, real64=True):
+    eng, orc = _engines(sc, real64)
+    ref = f.copy()
+    npo, rows = orc.analyze(cfg, sc.xyz_grid, ref, nthreads=4)
+    if cfg.tune_q:
+        O.tune_q(ref)
+    got = f.copy()
+    st = eng.analyze(cfg, sc.xyz_grid, got)
+    assert st.npts_analysed == npo and st.rows == rows
+    return got, ref, st
+
+
+def test_every_slot_fails_qc_leaves_field_untouched():
+    """Lists are non-empty but no slot survives `any(qc >= 0)` (core:429): p = 0 everywhere."""
+    sc, rng = S.scenario_tiny(k=8, n_dbz=0, n_vr=0)
+    for o in sc.obs.values():
+        if o.qc is not None:
+            o.qc[:] = -88
+    cfg = C.sample_namelist("T", use_radar=False)
+    f = S.make_field(rng, sc.k, sc.xyz_grid, 280.0, 5.0, 1.0)
+    got, ref, st = _field_parity(sc, cfg, f)
+    assert st.npts_analysed == 0 and np.array_equal(got, f) and np.array_equal(ref, f)
+
+
+def test_single_observation_scalar_update():
+    """One synop station, one assimilated slot: p = 1 at every point in range (the closed-form Kalman case)."""
+    rng = np.random.default_rng(2)
+    k = 6
+    sc = S.Scenario("one", 6, 6, 2, k, 3000.0, S.make_grid(6, 6, 2, 3000.0))
+    xyz = np.array([[500.0, -800.0, 900.0]], np.float32)
+    err = np.full((1, 5), 1.0, np.float32)
+    hdxb = (280.0 + rng.standard_normal((k, 1, 5))).astype(np.float32)
+    obs = np.full((1, 5), 281.0, np.float32)
+    qc = np.zeros((k, 1, 5), np.int32)
+    sc.obs[(C.GTS, 2)] = S.ObsSet(C.GTS, 2, 5, xyz, obs, hdxb, err, qc)     # synop: u, v, t, p, q
+    cfg = C.sample_namelist("T", use_radar=False)
+    for t in cfg.types:
+        if not (t.family == C.GTS and t.type == 2):
+            t.use_it = False
+        else:
+            t.is_assim = [False, False, True, False, False]
+    f = S.make_field(rng, k, sc.xyz_grid, 280.0, 2.0, 1.0)
+    got, ref, st = _field_parity(sc, cfg, f)
+    assert st.npts_analysed > 0 and st.rows == st.npts_analysed          # exactly one row per analysed point
+    scale = np.abs(ref).max()
+    assert np.abs(got - ref).max() <= 5e-7 * scale
+    _weights_case(sc, cfg, True, TOL64, npick=20)
+
+
+def test_rtps_zero_ensemble_nan_parity():
+    """RTPS divides by the analysis spread; an identically-zero ensemble at a point with local
+    obs gives 0/0 = NaN in the reference -- the NaNs must sit at the same points."""
+    sc, rng = S.scenario_tiny(k=16)
+    cfg = C.sample_namelist("QRAIN")
+    cfg.use_rtps, cfg.rtps_alpha, cfg.tune_q = True, 0.9, False
+    f = np.abs(S.make_field(rng, sc.k, sc.xyz_grid, 1e-3, 1e-3, 5e-4))
+    zero = rng.random(sc.npts) < 0.3
+    f[:, zero] = 0.0
+    got, ref, st = _field_parity(sc, cfg, f)
+    assert np.array_equal(np.isnan(got), np.isnan(ref))
+    assert np.isnan(ref).any(), "case must produce the 0/0"
+    ok = ~np.isnan(ref)
+    assert np.abs(got[ok] - ref[ok]).max() <= 5e-7 * np.abs(ref[ok]).max()
+
+
+def test_extreme_truncation_max_lz_pts_1():
+    """max_lz_pts = 1 keeps exactly the FIRST hit of the depth-first walk."""
+    sc, rng = S.scenario_tiny(k=8)
+    cfg = C.sample_namelist("T")
+    for t in cfg.types:
+        t.max_lz_pts = 1
+    eng, orc = _engines(sc)
+    got = eng.get_lz(cfg, sc.xyz_grid)
+    orc.build_tree(cfg)
+    for pt in range(0, sc.npts, 7):
+        for t, (fam, typ, idx, r2) in enumerate(orc.get_lz(sc.xyz_grid[pt])):
+            _, _, cnt, gidx, gr2 = got[t]
+            assert cnt[pt] == len(idx) <= 1
+            assert np.array_equal(gidx[pt, :cnt[pt]], idx)
+            assert np.array_equal(gr2[pt, :cnt[pt]].view(np.int32), r2.view(np.int32))
+
+
+def test_zero_points_and_empty_type():
+    """npts = 0 is a no-op; an observation type registered with n = 0 is ignored."""
+    sc, rng = S.scenario_tiny(k=8)
+    eng, _ = _engines(sc)
+    cfg = C.sample_namelist("T")
+    st = eng.analyze(cfg, np.zeros((0, 3), np.float32), np.zeros((sc.k, 0), np.float32))
+    assert st.npts == 0 and st.npts_analysed == 0
+    empty = S.ObsSet(C.GTS, 11, 5, np.zeros((0, 3), np.float32), np.zeros((0, 5), np.float32),
+                     np.zeros((sc.k, 0, 5), np.float32), np.zeros((0, 5), np.float32), np.zeros((sc.k, 0, 5), np.int32))
+    eng.set_obs(empty)
+    f = S.make_field(rng, sc.k, sc.xyz_grid, 280.0, 5.0, 1.0)
+    got = f.copy()
+    st = eng.analyze(cfg, sc.xyz_grid, got)
+    assert st.npts_analysed > 0
