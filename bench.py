@@ -50,9 +50,10 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
-    ap.add_argument("--nxb", type=int, default=16,
+    ap.add_argument("--nxb", type=int, default=0,
                     help="block size along x of the block-cyclic column decomposition (the reference's nxb, "
-                         "module_mpi_util.f90:10; results do not depend on it)")
+                         "module_mpi_util.f90:10; results do not depend on it); 0 = the largest of 16, 8, .. 1 "
+                         "that keeps the ranks balanced")
     ap.add_argument("--nyb", type=int, default=1)
     return ap.parse_args()
 
@@ -150,8 +151,11 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     from cwbnwp_letkf_b200 import config as C
+    from cwbnwp_letkf_b200 import partition as P
     from cwbnwp_letkf_b200 import synthetic as S
 
+    if a.nxb <= 0:
+        a.nxb = P.auto_block(a.nx, P.process_grid(world)[0])
     cfg = C.sample_namelist(a.var)
     cfg.tune_q = False if a.var == "T" else cfg.tune_q
     cfg._name = a.var

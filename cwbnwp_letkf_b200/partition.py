@@ -100,3 +100,18 @@ def local_index_tables(rank: int, world: int, nx: int, ny: int, nxb: int = 1, ny
     idx, idy = rank % npx, rank // npx
     return {"xloc": _block_cyclic(idx, nx, npx, nxb), "yloc": _block_cyclic(idy, ny, npy, nyb),
             "xloc_u": _block_cyclic(idx, nx + 1, npx, nxb), "yloc_v": _block_cyclic(idy, ny + 1, npy, nyb)}
+
+
+def auto_block(n: int, nproc: int, prefer: int = 16) -> int:
+    """Largest block size <= prefer (powers of two) whose block-cyclic split of n columns over nproc ranks
+    leaves the fullest rank within 2 % of the cyclic (block 1) split -- long blocks keep neighbouring
+    columns on one rank (warm starts), but a short grid must not lose its balance to them."""
+    def fullest(b):
+        return max(len(_block_cyclic(i, n, nproc, b)) for i in range(nproc))
+    base = fullest(1)
+    b = prefer
+    while b > 1:
+        if fullest(b) <= base * 1.02:
+            return b
+        b //= 2
+    return 1

@@ -72,3 +72,13 @@ def test_gloo_world2_allgather_members(k):
         p.join(120)
         assert p.exitcode == 0
     assert list(out) == [1] * world
+
+
+def test_auto_block_keeps_ranks_balanced():
+    from cwbnwp_letkf_b200 import partition as P
+    for n, npx in [(96, 4), (450, 4), (450, 2), (64, 4), (100, 4), (150, 2), (7, 4)]:
+        b = P.auto_block(n, npx)
+        sizes = [len(P._block_cyclic(i, n, npx, b)) for i in range(npx)]
+        cyc = [len(P._block_cyclic(i, n, npx, 1)) for i in range(npx)]
+        assert sum(sizes) == n and max(sizes) <= max(cyc) * 1.02 and b in (1, 2, 4, 8, 16)
+    assert P.auto_block(450, 4) == 16 and P.auto_block(96, 4) == 8
