@@ -327,7 +327,9 @@ static int64_t pick_chunk(letkf_b200_ctx *c, const std::vector<ActiveTree> &act,
   for (auto &a : act) per_pt += 4 + 8 * (size_t)a.tc->max_lz_pts;
   size_t free_b = 0, total_b = 0;
   LK_CUDA(cudaMemGetInfo(&free_b, &total_b));
-  const size_t budget = std::min<size_t>((size_t)12 << 30, free_b / 3);
+  // large chunks matter for large k: the persistent eigensolver grid quantises a chunk into rounds of
+  // 148 runs (k = 256: 530 KB per unit, 40 GB = 79k units = 33 rounds instead of 10)
+  const size_t budget = std::min<size_t>((size_t)40 << 30, free_b / 3);
   int64_t chunk = (int64_t)(budget / per_pt);
   chunk = std::max<int64_t>(1024, std::min<int64_t>(chunk, 1 << 18));
   return std::min<int64_t>(chunk, std::max<int64_t>(npts, 1));
