@@ -115,3 +115,76 @@ def auto_block(n: int, nproc: int, prefer: int = 16) -> int:
             return b
         b //= 2
     return 1
+
+
+# ---- letkf_scatter_grid / letkf_gather_grid as an all-to-all (module_mpi_util.f90:190-358) ------------
+# The reference keeps each member's full 3-D field on the rank that read it and transposes member-major
+# <-> column-major with mpi_alltoallv around the analysis of every variable (mpi:262,325).  Here rank r
+# holds members [lo_r, hi_r) of the full grid, `field[m, nz, ny, nx]`, and needs all k members of its own
+# columns, `var[k, nz, loc_ny, loc_nx]` -- exactly the `[k, npts]` array letkf_b200_analyze takes.  One
+# exchange per direction; NCCL over NVLink on GPUs, gloo in the CPU tests.
+def _exchange(send, recv):
+    import torch.distributed as dist
+    ops = []
+    for peer, t in recv.items():
+        ops.append(dist.P2POp(dist.irecv, t, peer))
+    for peer, t in send.items():
+        ops.append(dist.P2POp(dist.isend, t, peer))
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+
+
+def scatter_grid(field, k: int, rank: int, world: int, nxb: int = 1, nyb: int = 1, stagger: int = 0):
+    """field: torch tensor [m_r, nz, ny(+1), nx(+1)] (this rank's members of the full grid, x fastest).
+    Returns var [k, nz, loc_ny, loc_nx] with every member of the columns this rank owns.  stagger: 0 mass,
+    1 U (x extent nx+1), 2 V (y extent ny+1), as in letkf_scatter_grid."""
+    import torch
+    nz, nyy, nxx = field.shape[1:]
+    nx, ny = nxx - (1 if stagger == 1 else 0), nyy - (1 if stagger == 2 else 0)
+    xk, yk = ("xloc_u" if stagger == 1 else "xloc"), ("yloc_v" if stagger == 2 else "yloc")
+    tabs = [local_index_tables(r, world, nx, ny, nxb, nyb) for r in range(world)]
+    mine = tabs[rank]
+    lx, ly = len(mine[xk]), len(mine[yk])
+    var = torch.empty((k, nz, ly, lx), dtype=field.dtype, device=field.device)
+    send, recv = {}, {}
+    for r in range(world):
+        xi = torch.as_tensor(tabs[r][xk], device=field.device)
+        yj = torch.as_tensor(tabs[r][yk], device=field.device)
+        part = field.index_select(3, xi).index_select(2, yj).contiguous()     # [m_me, nz, ly_r, lx_r]
+        lo, hi = member_slice(r, world, k)
+        if r == rank:
+            var[lo:hi] = part
+        else:
+            send[r] = part
+            recv[r] = var[lo:hi]                                                  # contiguous slab of members
+    if world > 1:
+        _exchange(send, recv)
+    return var
+
+
+def gather_grid(var, field, k: int, rank: int, world: int, nxb: int = 1, nyb: int = 1, stagger: int = 0):
+    """Inverse of scatter_grid: writes the analysed columns of every rank back into this rank's members of
+    the full grid (in place; columns nobody analysed -- the last staggered column / row -- keep their values)."""
+    import torch
+    nz, nyy, nxx = field.shape[1:]
+    nx, ny = nxx - (1 if stagger == 1 else 0), nyy - (1 if stagger == 2 else 0)
+    xk, yk = ("xloc_u" if stagger == 1 else "xloc"), ("yloc_v" if stagger == 2 else "yloc")
+    tabs = [local_index_tables(r, world, nx, ny, nxb, nyb) for r in range(world)]
+    lo, hi = member_slice(rank, world, k)
+    send, recv = {}, {}
+    for r in range(world):
+        lx, ly = len(tabs[r][xk]), len(tabs[r][yk])
+        if r == rank:
+            recv[r] = var[lo:hi]
+        else:
+            send[r] = var[slice(*member_slice(r, world, k))].contiguous()
+            recv[r] = torch.empty((hi - lo, nz, ly, lx), dtype=var.dtype, device=var.device)
+    if world > 1:
+        _exchange(send, {r: t for r, t in recv.items() if r != rank})
+    for r in range(world):
+        xi = torch.as_tensor(tabs[r][xk], device=field.device)
+        yj = torch.as_tensor(tabs[r][yk], device=field.device)
+        idx = (yj[:, None] * nxx + xi[None, :]).reshape(-1)
+        field.view(hi - lo, nz, nyy * nxx).index_copy_(2, idx, recv[r].reshape(hi - lo, nz, -1))
+    return field

@@ -82,3 +82,46 @@ def test_auto_block_keeps_ranks_balanced():
         cyc = [len(P._block_cyclic(i, n, npx, 1)) for i in range(npx)]
         assert sum(sizes) == n and max(sizes) <= max(cyc) * 1.02 and b in (1, 2, 4, 8, 16)
     assert P.auto_block(450, 4) == 16 and P.auto_block(96, 4) == 8
+
+
+def _a2a_worker(rank, world, port, k, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    ok = True
+    nx, ny, nz = 9, 6, 3
+    for stagger, nxb in ((0, 1), (1, 2), (2, 1)):
+        nxx, nyy = nx + (stagger == 1), ny + (stagger == 2)
+        g = torch.Generator().manual_seed(5)
+        full = torch.randn((k, nz, nyy, nxx), generator=g)                    # the same on every rank
+        lo, hi = P.member_slice(rank, world, k)
+        var = P.scatter_grid(full[lo:hi].clone(), k, rank, world, nxb=nxb, stagger=stagger)
+        t = P.local_index_tables(rank, world, nx, ny, nxb, 1)
+        xi = torch.as_tensor(t["xloc_u" if stagger == 1 else "xloc"])
+        yj = torch.as_tensor(t["yloc_v" if stagger == 2 else "yloc"])
+        ok = ok and torch.equal(var, full.index_select(3, xi).index_select(2, yj))
+        # "analysis": every rank adds its rank + 1 to its columns; the gathered grid must show the owner map
+        mine = full[lo:hi].clone()
+        P.gather_grid(var + (rank + 1), mine, k, rank, world, nxb=nxb, stagger=stagger)
+        owner = torch.zeros((nyy, nxx))
+        for r in range(world):
+            tr = P.local_index_tables(r, world, nx, ny, nxb, 1)
+            xr = torch.as_tensor(tr["xloc_u" if stagger == 1 else "xloc"])
+            yr = torch.as_tensor(tr["yloc_v" if stagger == 2 else "yloc"])
+            owner[yr[:, None], xr[None, :]] = r + 1
+        ok = ok and torch.allclose(mine - full[lo:hi], owner.expand(hi - lo, nz, nyy, nxx))
+        ok = ok and bool((owner > 0).all())
+    out[rank] = int(ok)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("k", [8, 5])
+def test_gloo_world2_scatter_gather_grid(k):
+    """letkf_scatter_grid / letkf_gather_grid (module_mpi_util.f90:190-358) as one exchange per direction."""
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    out = mp.get_context("spawn").Manager().dict()
+    mp.spawn(_a2a_worker, args=(2, port, k, out), nprocs=2, join=True)
+    assert out[0] == 1 and out[1] == 1
