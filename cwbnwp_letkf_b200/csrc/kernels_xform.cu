@@ -206,6 +206,40 @@ __global__ void __launch_bounds__(256) fma_peak_kernel(T *out, int iters) {
   if (s == (T)123.456) out[0] = s;
 }
 
+// kind 2: FP64 tensor pipe alone (mma.sync.m8n8k4.f64, 8 independent accumulator tiles per warp);
+// kind 3: the same DMMA stream interleaved with an equal number of independent DFMA chains in every warp --
+// tells whether the FP64 tensor pipe and the FP64 FMA pipe overlap on this GPU (reported: DMMA flop + FMA flop).
+template <bool WITH_FMA>
+__global__ void __launch_bounds__(256) dmma_peak_kernel(double *out, int iters) {
+  double c[8][2], a[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    c[i][0] = c[i][1] = 0.0;
+    a[i] = (threadIdx.x + i) * 1e-3;
+  }
+  const double fa = 1.0 + 1e-9 * threadIdx.x, fb = 1e-9, x = 1.0000001, y = 1e-7;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                     : "+d"(c[i][0]), "+d"(c[i][1])
+                     : "d"(fa), "d"(fb));
+      if (WITH_FMA) {
+#pragma unroll
+        for (int q = 0; q < 2; ++q)
+#pragma unroll
+          for (int i = 0; i < 8; ++i) a[i] = a[i] * x + y;
+      }
+    }
+  }
+  double sacc = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) sacc += c[i][0] + c[i][1] + a[i];
+  if (sacc == 123.456) out[0] = sacc;
+}
+
 double run_fma_peak(cudaStream_t s, int kind) {
   int dev = 0, sms = 0;
   LK_CUDA(cudaGetDevice(&dev));
@@ -215,20 +249,26 @@ double run_fma_peak(cudaStream_t s, int kind) {
   cudaEvent_t e0, e1;
   LK_CUDA(cudaEventCreate(&e0));
   LK_CUDA(cudaEventCreate(&e1));
-  const int blocks = sms * 8, iters = kind == 0 ? 4000 : 16000;
+  const int blocks = sms * 8, iters = kind == 0 ? 4000 : (kind == 1 ? 16000 : 2000);
   double best = 0;
   for (int rep = 0; rep < 4; ++rep) {
     LK_CUDA(cudaEventRecord(e0, s));
     if (kind == 0)
       fma_peak_kernel<double><<<blocks, 256, 0, s>>>((double *)out, iters);
-    else
+    else if (kind == 1)
       fma_peak_kernel<float><<<blocks, 256, 0, s>>>((float *)out, iters);
+    else if (kind == 2)
+      dmma_peak_kernel<false><<<blocks, 256, 0, s>>>((double *)out, iters);
+    else
+      dmma_peak_kernel<true><<<blocks, 256, 0, s>>>((double *)out, iters);
     launch_counter()++;
     LK_CUDA(cudaEventRecord(e1, s));
     LK_CUDA(cudaEventSynchronize(e1));
     float ms = 0;
     LK_CUDA(cudaEventElapsedTime(&ms, e0, e1));
-    const double flops = 2.0 * 64.0 * iters * 256.0 * blocks;
+    // per thread and iteration: 64 FMA (kinds 0, 1); 32 DMMA of 2*8*8*4/32 flop per lane (+ 64 FMA, kind 3)
+    const double per_thread = kind <= 1 ? 2.0 * 64.0 : (32.0 * 16.0 + (kind == 3 ? 2.0 * 64.0 : 0.0));
+    const double flops = per_thread * iters * 256.0 * blocks;
     if (rep > 0) best = std::max(best, flops / (ms * 1e-3) / 1e12);
   }
   cudaEventDestroy(e0);

@@ -168,7 +168,8 @@ int letkf_b200_syevd_batched_dev(letkf_b200_ctx *ctx, int k, int64_t batch, int 
                                  const void *A, void *W, void *V, int32_t *sweeps);
 
 /* device FMA-peak micro-benchmark (roofline denominator of the eigen stage): returns the
- * sustained TFLOP/s of dependent-chain-free FMA loops.  kind: 0 = FP64 FMA, 1 = FP32 FMA */
+ * sustained TFLOP/s of dependent-chain-free FMA loops.  kind: 0 = FP64 FMA, 1 = FP32 FMA,
+ * 2 = FP64 tensor pipe (mma.sync.m8n8k4.f64), 3 = 2 and 0 interleaved in every warp (sum of both) */
 int letkf_b200_fma_peak(letkf_b200_ctx *ctx, int kind, double *tflops);
 
 /* Host-only self-test, no GPU needed and NOT part of any product path: builds the k-d tree of one
