@@ -407,7 +407,7 @@ def main():
            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
            "stages": stage, "points_analysed": int(analysed), "analysed_fraction": analysed / total_pts,
            "points_per_s_analysed_only": analysed / (ms_per_step * 1e-3), "rows_per_analysed_point": rows / max(analysed, 1),
-           "fma_peak_tflops": {"fp64": fma64, "fp32": fma32, "fp64_dmma": dmma64, "fp64_dmma_plus_fma": mixed64}, "obs_setup_s": t_obs, "wall_s_timed": wall,
+           "ms_steps": [round(float(x), 2) for x in t_steps], "fma_peak_tflops": {"fp64": fma64, "fp32": fma32, "fp64_dmma": dmma64, "fp64_dmma_plus_fma": mixed64}, "obs_setup_s": t_obs, "wall_s_timed": wall,
            "obs_values": sc.total_obs_values()}
     print(json.dumps(out))
     if world > 1:
