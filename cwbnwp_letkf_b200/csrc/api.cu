@@ -49,6 +49,7 @@ struct letkf_b200_ctx {
   DevBuf<int64_t> rows_sum;
   DevBuf<unsigned char> cub_tmp;
   DevBuf<unsigned char> C, b, lam, wbar;  // sized in bytes for the working precision
+  std::vector<cudaEvent_t> io_ev;         // chunk-granular host IO: [2*i] upload done, [2*i+1] chunk analysed
 };
 
 template <typename F>
@@ -97,6 +98,7 @@ extern "C" int letkf_b200_finalize(letkf_b200_ctx *c) {
     for (auto &ev : c->ev)
       if (ev) cudaEventDestroy(ev);
     cudaStreamDestroy(c->stream);
+    for (auto &ev : c->io_ev) cudaEventDestroy(ev);
     if (c->cs_in) {
       cudaStreamDestroy(c->cs_in);
       cudaStreamDestroy(c->cs_out);
@@ -341,6 +343,11 @@ struct ChunkOut {  // optional parity outputs of run_pipeline
   double *Wa = nullptr;       // device [npts][k][k]
   double *xa_raw = nullptr;   // device [npts][k]
   bool transform = true;
+  // Host-pointer call: the ensemble fields stay on the host and are moved chunk by chunk -- chunk i+1..
+  // uploads and chunk i-1 downloads run on two copy streams while chunk i is analysed (rows of the
+  // member-slowest [nfields*k][npts] matrix: one 2-D copy per chunk and direction).
+  const float *h_in = nullptr;  // host var, read
+  float *h_out = nullptr;       // host var, written (chunks that were analysed)
 };
 
 template <typename T>
@@ -380,8 +387,25 @@ static void run_pipeline(letkf_b200_ctx *c, const letkf_b200_var_config *cfg, in
     LK_CUDA(cudaMemsetAsync(c->counters.p, 0, 4 * sizeof(int32_t), s));
     const float inflat = LK_DIV((float)(k - 1), cfg->multi_infl);  // core:68 (real32)
     const T mu = (T)inflat;                                       // core:645
+    const bool host_io = co.h_in != nullptr && nz == 1 && nfields > 0;
+    const int io_rows = nfields * k;
+    if (host_io) {
+      const int64_t nchunks = (nsearch + chunk - 1) / chunk;
+      while ((int64_t)c->io_ev.size() < 2 * nchunks) {
+        cudaEvent_t e;
+        LK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        c->io_ev.push_back(e);
+      }
+      for (int64_t ci = 0; ci < nchunks; ++ci) {  // all uploads are queued now; they stream in chunk order
+        const int64_t c0 = ci * chunk, nq = std::min(chunk, nsearch - c0);
+        LK_CUDA(cudaMemcpy2DAsync(d_var + c0, sizeof(float) * npts, co.h_in + c0, sizeof(float) * npts,
+                                  sizeof(float) * nq, io_rows, cudaMemcpyHostToDevice, c->cs_in));
+        LK_CUDA(cudaEventRecord(c->io_ev[2 * ci], c->cs_in));
+      }
+    }
     for (int64_t c0 = 0; c0 < nsearch; c0 += chunk) {
       const int64_t nq = std::min(chunk, nsearch - c0);
+      const int64_t ci = c0 / chunk;
       LK_CUDA(cudaEventRecord(c->ev[2], s));
       for (int t = 0; t < tv.ntrees; ++t) launch_search(s, tv.t[t], nq, d_xyz + c0 * 3);
       launch_count_rows(s, tv, nq, c->p.p);
@@ -402,6 +426,7 @@ static void run_pipeline(letkf_b200_ctx *c, const letkf_b200_var_config *cfg, in
       stats.rows += h_rows * nz;
       if (co.p) LK_CUDA(cudaMemcpyAsync(co.p + c0, c->p.p, sizeof(int32_t) * nq, cudaMemcpyDeviceToDevice, s));
       if (nunits > 0) {
+        if (host_io) LK_CUDA(cudaStreamWaitEvent(s, c->io_ev[2 * ci], 0));  // this chunk's fields are in HBM
         c->C.ensure((size_t)nunits * k * k * sizeof(T));
         c->b.ensure((size_t)nunits * k * sizeof(T));
         c->lam.ensure((size_t)nunits * k * sizeof(T));
@@ -463,6 +488,12 @@ static void run_pipeline(letkf_b200_ctx *c, const letkf_b200_var_config *cfg, in
         }
         }
         LK_CUDA(cudaEventRecord(c->ev[6], s));
+        if (host_io) {  // hand the analysed chunk to the download stream (unanalysed chunks are unchanged)
+          LK_CUDA(cudaEventRecord(c->io_ev[2 * ci + 1], s));
+          LK_CUDA(cudaStreamWaitEvent(c->cs_out, c->io_ev[2 * ci + 1], 0));
+          LK_CUDA(cudaMemcpy2DAsync(co.h_out + c0, sizeof(float) * npts, d_var + c0, sizeof(float) * npts,
+                                    sizeof(float) * nq, io_rows, cudaMemcpyDeviceToHost, c->cs_out));
+        }
         LK_CUDA(cudaEventSynchronize(c->ev[6]));
         float ms = 0;
         LK_CUDA(cudaEventElapsedTime(&ms, c->ev[3], c->ev[4]));
@@ -475,6 +506,10 @@ static void run_pipeline(letkf_b200_ctx *c, const letkf_b200_var_config *cfg, in
       float ms = 0;
       LK_CUDA(cudaEventElapsedTime(&ms, c->ev[2], c->ev[3]));
       ms_search += ms;
+    }
+    if (host_io) {
+      LK_CUDA(cudaStreamSynchronize(c->cs_in));
+      LK_CUDA(cudaStreamSynchronize(c->cs_out));
     }
     if (cfg->tune_q && co.transform)
       for (int f = 0; f < nfields; ++f) launch_tune_q(s, k, npts, d_var + (int64_t)f * npts * k);  // core:252-278
@@ -513,8 +548,20 @@ extern "C" int letkf_b200_analyze_dev(letkf_b200_ctx *c, const letkf_b200_var_co
   return guarded([&] { analyze_dev_impl(c, cfg, npts, xyz, nfields, var, st); });
 }
 
-// Host-pointer entry point.  By default the whole grid is copied in, analysed and copied out (on a
-// B200 host the two transfers of config M cost ~60 ms of a 1.4 s step).  With LETKF_B200_SLAB=<points>
+static void ensure_copy_streams(letkf_b200_ctx *c) {
+  if (c->cs_in) return;
+  LK_CUDA(cudaStreamCreateWithFlags(&c->cs_in, cudaStreamNonBlocking));
+  LK_CUDA(cudaStreamCreateWithFlags(&c->cs_out, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; ++i) {
+    LK_CUDA(cudaEventCreateWithFlags(&c->ev_in[i], cudaEventDisableTiming));
+    LK_CUDA(cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming));
+    LK_CUDA(cudaEventCreateWithFlags(&c->ev_out[i], cudaEventDisableTiming));
+  }
+}
+
+// Host-pointer entry point.  By default the coordinates are copied in and the fields stream through the
+// device chunk by chunk on two copy streams while other chunks are analysed (on a B200 host the two bulk
+// transfers of config M cost ~50 ms of a 1.3 s step when they are not overlapped).  With LETKF_B200_SLAB=<points>
 // the grid is instead streamed through double-buffered slabs (slab i+1 copied in and slab i-1 copied
 // out on two copy streams while slab i is analysed) -- for grids that do not fit in HBM; measured
 // slower than the single pass when everything fits (per-slab overheads > hidden copy time).  Points
@@ -535,6 +582,22 @@ extern "C" int letkf_b200_analyze(letkf_b200_ctx *c, const letkf_b200_var_config
       c->d_xyz.ensure((size_t)npts * 3 + 1);
       c->d_var.ensure(nv + 1);
       LK_CUDA(cudaMemcpyAsync(c->d_xyz.p, xyz, sizeof(float) * 3 * npts, cudaMemcpyHostToDevice, c->stream));
+      // The fields move chunk by chunk on two copy streams, overlapped with the analysis of the other chunks
+      // (run_pipeline).  Not when all levels of a column share weights or tune_q post-processes the whole
+      // field: then one copy in, one copy out.
+      const bool chunk_io = c->nz_hint == 1 && !cfg->tune_q && nfields > 0 && npts > 0 && !getenv("LETKF_B200_BULK_IO");
+      if (chunk_io) {
+        ensure_copy_streams(c);
+        ChunkOut co;
+        co.h_in = var;
+        co.h_out = var;
+        if (c->real64)
+          run_pipeline<double>(c, cfg, npts, c->d_xyz.p, nfields, c->d_var.p, st, co);
+        else
+          run_pipeline<float>(c, cfg, npts, c->d_xyz.p, nfields, c->d_var.p, st, co);
+        LK_CUDA(cudaStreamSynchronize(c->stream));
+        return;
+      }
       LK_CUDA(cudaMemcpyAsync(c->d_var.p, var, sizeof(float) * nv, cudaMemcpyHostToDevice, c->stream));
       analyze_dev_impl(c, cfg, npts, c->d_xyz.p, nfields, c->d_var.p, st);
       LK_CUDA(cudaMemcpyAsync(var, c->d_var.p, sizeof(float) * nv, cudaMemcpyDeviceToHost, c->stream));
@@ -542,15 +605,7 @@ extern "C" int letkf_b200_analyze(letkf_b200_ctx *c, const letkf_b200_var_config
       return;
     }
     const int rows = nfields * k;  // field f, member m is row f*k+m of a [rows][npts] host matrix
-    if (!c->cs_in) {
-      LK_CUDA(cudaStreamCreateWithFlags(&c->cs_in, cudaStreamNonBlocking));
-      LK_CUDA(cudaStreamCreateWithFlags(&c->cs_out, cudaStreamNonBlocking));
-      for (int i = 0; i < 2; ++i) {
-        LK_CUDA(cudaEventCreateWithFlags(&c->ev_in[i], cudaEventDisableTiming));
-        LK_CUDA(cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming));
-        LK_CUDA(cudaEventCreateWithFlags(&c->ev_out[i], cudaEventDisableTiming));
-      }
-    }
+    ensure_copy_streams(c);
     for (int i = 0; i < 2; ++i) {
       c->slab_xyz[i].ensure((size_t)slab * 3);
       c->slab_var[i].ensure((size_t)slab * rows + 1);
