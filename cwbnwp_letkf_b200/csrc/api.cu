@@ -403,6 +403,19 @@ static void run_pipeline(letkf_b200_ctx *c, const letkf_b200_var_config *cfg, in
         LK_CUDA(cudaEventRecord(c->io_ev[2 * ci], c->cs_in));
       }
     }
+    // letkf_tune_q is pointwise, so with chunked host IO it runs per chunk, before the chunk is downloaded
+    const bool tq_chunk = host_io && cfg->tune_q && co.transform;
+    // hand a finished chunk to the download stream (chunks that were not analysed are unchanged on the
+    // host, unless tune_q touches every point)
+    auto chunk_out = [&](int64_t ci, int64_t c0, int64_t nq, bool need_upload_wait) {
+      if (need_upload_wait) LK_CUDA(cudaStreamWaitEvent(s, c->io_ev[2 * ci], 0));
+      if (tq_chunk)
+        for (int f = 0; f < nfields; ++f) launch_tune_q(s, k, npts, d_var + (int64_t)f * npts * k, c0, nq);
+      LK_CUDA(cudaEventRecord(c->io_ev[2 * ci + 1], s));
+      LK_CUDA(cudaStreamWaitEvent(c->cs_out, c->io_ev[2 * ci + 1], 0));
+      LK_CUDA(cudaMemcpy2DAsync(co.h_out + c0, sizeof(float) * npts, d_var + c0, sizeof(float) * npts,
+                                sizeof(float) * nq, io_rows, cudaMemcpyDeviceToHost, c->cs_out));
+    };
     for (int64_t c0 = 0; c0 < nsearch; c0 += chunk) {
       const int64_t nq = std::min(chunk, nsearch - c0);
       const int64_t ci = c0 / chunk;
@@ -488,12 +501,7 @@ static void run_pipeline(letkf_b200_ctx *c, const letkf_b200_var_config *cfg, in
         }
         }
         LK_CUDA(cudaEventRecord(c->ev[6], s));
-        if (host_io) {  // hand the analysed chunk to the download stream (unanalysed chunks are unchanged)
-          LK_CUDA(cudaEventRecord(c->io_ev[2 * ci + 1], s));
-          LK_CUDA(cudaStreamWaitEvent(c->cs_out, c->io_ev[2 * ci + 1], 0));
-          LK_CUDA(cudaMemcpy2DAsync(co.h_out + c0, sizeof(float) * npts, d_var + c0, sizeof(float) * npts,
-                                    sizeof(float) * nq, io_rows, cudaMemcpyDeviceToHost, c->cs_out));
-        }
+        if (host_io) chunk_out(ci, c0, nq, false);
         LK_CUDA(cudaEventSynchronize(c->ev[6]));
         float ms = 0;
         LK_CUDA(cudaEventElapsedTime(&ms, c->ev[3], c->ev[4]));
@@ -503,6 +511,9 @@ static void run_pipeline(letkf_b200_ctx *c, const letkf_b200_var_config *cfg, in
         LK_CUDA(cudaEventElapsedTime(&ms, c->ev[5], c->ev[6]));
         ms_xf += ms;
       }
+      else if (host_io && tq_chunk) {
+        chunk_out(ci, c0, nq, true);
+      }
       float ms = 0;
       LK_CUDA(cudaEventElapsedTime(&ms, c->ev[2], c->ev[3]));
       ms_search += ms;
@@ -511,7 +522,7 @@ static void run_pipeline(letkf_b200_ctx *c, const letkf_b200_var_config *cfg, in
       LK_CUDA(cudaStreamSynchronize(c->cs_in));
       LK_CUDA(cudaStreamSynchronize(c->cs_out));
     }
-    if (cfg->tune_q && co.transform)
+    if (cfg->tune_q && co.transform && !tq_chunk)
       for (int f = 0; f < nfields; ++f) launch_tune_q(s, k, npts, d_var + (int64_t)f * npts * k);  // core:252-278
     int32_t h_sw[2] = {0, 0};
     LK_CUDA(cudaMemcpyAsync(h_sw, c->counters.p + 1, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
@@ -583,9 +594,8 @@ extern "C" int letkf_b200_analyze(letkf_b200_ctx *c, const letkf_b200_var_config
       c->d_var.ensure(nv + 1);
       LK_CUDA(cudaMemcpyAsync(c->d_xyz.p, xyz, sizeof(float) * 3 * npts, cudaMemcpyHostToDevice, c->stream));
       // The fields move chunk by chunk on two copy streams, overlapped with the analysis of the other chunks
-      // (run_pipeline).  Not when all levels of a column share weights or tune_q post-processes the whole
-      // field: then one copy in, one copy out.
-      const bool chunk_io = c->nz_hint == 1 && !cfg->tune_q && nfields > 0 && npts > 0 && !getenv("LETKF_B200_BULK_IO");
+      // (run_pipeline).  Not when all levels of a column share weights: then one copy in, one copy out.
+      const bool chunk_io = c->nz_hint == 1 && nfields > 0 && npts > 0 && !getenv("LETKF_B200_BULK_IO");
       if (chunk_io) {
         ensure_copy_streams(c);
         ChunkOut co;

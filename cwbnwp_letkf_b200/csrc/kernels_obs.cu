@@ -188,9 +188,11 @@ void launch_yoyb_rows(cudaStream_t s, const TreeViews &tv, int k, int64_t nq, co
 // ---- letkf_tune_q (module_letkf_core.f90:702-733) ---------------------------------------------
 // One thread per grid point: coalesced across points for every member.  ratio = sum(var) /
 // sum(var, var>0) in real32, sequential over members; 0/0 -> NaN like the reference.
-__global__ void tune_q_kernel(int k, int64_t npts, float *__restrict__ var) {
-  const int64_t pt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (pt >= npts) return;
+// Points [p0, p0 + n) of a field whose member stride is npts.
+__global__ void tune_q_kernel(int k, int64_t npts, int64_t p0, int64_t n, float *__restrict__ var) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int64_t pt = p0 + i;
   float s_all = 0.f, s_pos = 0.f;
   for (int m = 0; m < k; ++m) {
     const float v = var[(int64_t)m * npts + pt];
@@ -204,10 +206,11 @@ __global__ void tune_q_kernel(int k, int64_t npts, float *__restrict__ var) {
   }
 }
 
-void launch_tune_q(cudaStream_t s, int k, int64_t npts, float *var) {
-  if (npts == 0) return;
+void launch_tune_q(cudaStream_t s, int k, int64_t npts, float *var, int64_t p0, int64_t n) {
+  if (n < 0) n = npts - p0;
+  if (n <= 0) return;
   const int bs = 256;
-  tune_q_kernel<<<(unsigned)((npts + bs - 1) / bs), bs, 0, s>>>(k, npts, var);
+  tune_q_kernel<<<(unsigned)((n + bs - 1) / bs), bs, 0, s>>>(k, npts, p0, n, var);
   launch_counter()++;
   LK_CUDA(cudaGetLastError());
 }

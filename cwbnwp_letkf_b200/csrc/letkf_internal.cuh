@@ -171,7 +171,7 @@ void launch_transform(cudaStream_t s, int k, int64_t nunits, const int32_t *unit
 template <typename T>
 void launch_weights_dump(cudaStream_t s, int k, int64_t nunits, const int32_t *unit_pt, const T *U,
                          const T *lam, const T *wbar, double *wbar_out, double *Wa_out);
-void launch_tune_q(cudaStream_t s, int k, int64_t npts, float *var);
+void launch_tune_q(cudaStream_t s, int k, int64_t npts, float *var, int64_t p0 = 0, int64_t n = -1);
 void launch_yoyb_rows(cudaStream_t s, const TreeViews &tv, int k, int64_t nq, const int64_t *row_offset,
                       float *yo, float *yb);
 double run_fma_peak(cudaStream_t s, int kind);
