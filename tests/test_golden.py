@@ -1,28 +1,36 @@
-"""Golden vectors (tests/golden/tiny_T_k8.npz, produced by tests/golden/make_golden.py from the oracle:
-the Fortran reference cannot be executed here).  CPU tier: the oracle still reproduces them bit for bit.
-GPU tier: the CUDA path reproduces the lists / rows bit for bit and the analysis to real32 rounding."""
+"""Golden vectors (tests/golden/*.npz, produced by tests/golden/make_golden.py from the oracle: the Fortran
+reference cannot be executed here).  CPU tier: the oracle still reproduces them bit for bit.
+GPU tier: the CUDA path reproduces the lists / rows bit for bit and the analysis to real32 rounding, NaNs
+(real32 Gaspari-Cohn, tune_q 0/0) at the same places."""
 import os
+import sys
 
 import numpy as np
 import pytest
 
-from cwbnwp_letkf_b200 import config as C
-from cwbnwp_letkf_b200 import synthetic as S
-
 HERE = os.path.dirname(os.path.abspath(__file__))
-G = np.load(os.path.join(HERE, "golden", "tiny_T_k8.npz"))
+sys.path.insert(0, os.path.join(HERE, "golden"))
+import make_golden as MG  # noqa: E402
+
+NAMES = list(MG.CASES)
 
 
-def _case():
-    sc, rng = S.scenario_tiny(k=8)
-    field = S.make_field(rng, sc.k, sc.xyz_grid, 280.0, 5.0, 1.0)
-    assert np.array_equal(field, G["field_in"]), "synthetic generator changed: regenerate the golden file"
-    return sc, C.sample_namelist("T"), field
+def _load(name):
+    G = np.load(os.path.join(HERE, "golden", name + ".npz"))
+    sc, cfg, field = MG.case_inputs(name)
+    assert np.array_equal(field, G["field_in"]), "synthetic generator changed: regenerate the golden files"
+    return G, sc, cfg, field
 
 
-def test_oracle_reproduces_golden_vectors():
+def _bits_equal(a, b):
+    na, nb = np.isnan(a), np.isnan(b)
+    return np.array_equal(na, nb) and np.array_equal(a[~na].view(np.int32), b[~nb].view(np.int32))
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_oracle_reproduces_golden_vectors(name):
     from oracle import oracle as O
-    sc, cfg, field = _case()
+    G, sc, cfg, field = _load(name)
     orc = O.Oracle(sc.k, True)
     for o in sc.obs.values():
         orc.set_obs(o)
@@ -32,18 +40,30 @@ def test_oracle_reproduces_golden_vectors():
             assert np.array_equal(idx, G[f"idx_{pt}_{t}"])
             assert np.array_equal(r2.view(np.int32), G[f"r2_{pt}_{t}"].view(np.int32))
         yo, yb = orc.letkf_yoyb(sc.xyz_grid[pt])
-        assert np.array_equal(yo.view(np.int32), G[f"yo_{pt}"].view(np.int32))
-        assert np.array_equal(yb.view(np.int32), G[f"yb_{pt}"].view(np.int32))
+        assert _bits_equal(yo, G[f"yo_{pt}"]) and _bits_equal(yb, G[f"yb_{pt}"])
     ana = field.copy()
     npo, rows = orc.analyze(cfg, sc.xyz_grid, ana, nthreads=2)
+    if cfg.tune_q:
+        O.tune_q(ana)
     assert [npo, rows] == list(G["counts"])
-    assert np.array_equal(ana.view(np.int32), G["analysis"].view(np.int32))
+    assert _bits_equal(ana, G["analysis"])
+
+
+def test_golden_cases_exercise_the_hazards():
+    """The fixtures are only useful if they contain what they claim to pin."""
+    G = np.load(os.path.join(HERE, "golden", "tiny_QRAIN_gc_k8.npz"))
+    assert np.isnan(G["analysis"]).any()                         # real32 Gaspari-Cohn / tune_q NaNs
+    assert any(np.isnan(G[f"yb_{pt}"]).any() for pt in G["pts"]) or np.isnan(G["analysis"]).any()
+    G = np.load(os.path.join(HERE, "golden", "tiny_T_k8.npz"))
+    assert max(len(G[k]) for k in G.files if k.startswith("idx_")) == 300   # truncation at max_lz_pts (vr)
+    assert G["counts"][0] > 0
 
 
 @pytest.mark.gpu
-def test_cuda_path_reproduces_golden_vectors():
+@pytest.mark.parametrize("name", NAMES)
+def test_cuda_path_reproduces_golden_vectors(name):
     from cwbnwp_letkf_b200 import host as H
-    sc, cfg, field = _case()
+    G, sc, cfg, field = _load(name)
     eng = H.LetkfB200(sc.k, True)
     for o in sc.obs.values():
         eng.set_obs(o)
@@ -54,10 +74,11 @@ def test_cuda_path_reproduces_golden_vectors():
             assert np.array_equal(idx[pt, :cnt[pt]], G[f"idx_{pt}_{t}"])
             assert np.array_equal(r2[pt, :cnt[pt]].view(np.int32), G[f"r2_{pt}_{t}"].view(np.int32))
         a, b = off[pt], off[pt + 1]
-        assert np.array_equal(yo[a:b].view(np.int32), G[f"yo_{pt}"].view(np.int32))
-        assert np.array_equal(yb[a:b].view(np.int32), G[f"yb_{pt}"].view(np.int32))
+        assert _bits_equal(yo[a:b], G[f"yo_{pt}"]) and _bits_equal(yb[a:b], G[f"yb_{pt}"])
     ana = field.copy()
-    st = eng.analyze(cfg, sc.xyz_grid, ana)
+    st = eng.analyze(cfg, sc.xyz_grid, ana)                       # applies tune_q when cfg.tune_q is set
     assert [st.npts_analysed, st.rows] == list(G["counts"])
     ref = G["analysis"]
-    assert (ana == ref).mean() > 0.98 and np.abs(ana - ref).max() <= 5e-7 * np.abs(ref).max()
+    assert np.array_equal(np.isnan(ana), np.isnan(ref))
+    ok = ~np.isnan(ref)
+    assert (ana[ok] == ref[ok]).mean() > 0.98 and np.abs(ana[ok] - ref[ok]).max() <= 5e-7 * np.abs(ref[ok]).max()
