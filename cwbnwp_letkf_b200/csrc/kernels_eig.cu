@@ -476,199 +476,199 @@ __global__ void __launch_bounds__(RPL >= 5 ? 256 : 512)
     __syncthreads();
   }
   for (int64_t rb = blockIdx.x; rb * run < n; rb += gridDim.x) {
-  const int64_t u0 = rb * run, u1 = u0 + run < n ? u0 + run : n;
-  bool prev_ok = false;
-  for (int64_t u = u0; u < u1; ++u) {
-  T *Gg = MODE == 0 ? Cio + u * (int64_t)k * k : Vout + u * (int64_t)k * k;
-  T *G = SMEM ? Gs : Gg;
-  const bool warm = can_chain && prev_ok;
-  const T *Up = MODE == 0 && u > u0 ? Cio + (u - 1) * (int64_t)k * k : nullptr;  // U of the previous unit
-  if (MODE == 0) {
-    __syncthreads();
-    if (SMEM)  // Gram kernels deliver the column-major lower triangle: symmetrise while loading
-      for (int e = tid; e < k * k; e += nt) {
-        const int i = e % k, j = e / k;
-        G[i + (size_t)j * ld] = i >= j ? Gg[i + (size_t)j * k] : Gg[j + (size_t)i * k];
-      }
-    if (tid == 0) s_shift = T(0);
-    __syncthreads();
-    if (warm && chain_big) {
-      // S = C U_prev, then C' = U_prev^T S -> G (C: full in shared memory, lower triangle in global)
-      block_gemm_dmma_oop<T>(
-          [&](int i, int l) {
-            return SMEM ? (double)G[i + (size_t)l * ld] : (double)(i >= l ? G[i + (size_t)l * ld] : G[l + (size_t)i * ld]);
-          },
-          [&](int l, int j) { return (double)Up[l + (size_t)j * k]; }, S, k, k);
-      block_gemm_dmma_oop<T>([&](int i, int l) { return (double)Up[l + (size_t)i * k]; },
-                             [&](int l, int j) { return (double)S[l + (size_t)j * k]; }, G, ld, k);
-    } else if (warm) {
-      // T = C U_prev, then C' = U_prev^T T (both written over G)
-      block_gemm_dmma<T>([&](int i, int l) { return (double)G[i + (size_t)l * ld]; },
-                         [&](int l, int j) { return (l < k && j < k) ? (double)Up[l + (size_t)j * k] : 0.0; }, G, ld, kp);
-      block_gemm_dmma<T>([&](int i, int l) { return (l < k && i < k) ? (double)Up[l + (size_t)i * k] : 0.0; },
-                         [&](int l, int j) { return (double)G[l + (size_t)j * ld]; }, G, ld, kp);
-    }
-    // C is SPD by construction; a NaN input propagates
-    if (SMEM)
-      block_cholesky(G, k, ld);
-    else
-      block_cholesky_panel(G, k, Gs);
-  } else {
-    const T *A = Ain + u * (int64_t)k * k;
-    // First try the matrix as it is (an SPD input keeps its full relative accuracy); if a pivot
-    // fails, shift by a Gershgorin bound so that it becomes definite and factor again.
-    for (int attempt = 0; attempt < 2; ++attempt) {
-      __syncthreads();
-      for (int e = tid; e < k * k; e += nt) {  // symmetrise from the lower triangle
-        const int i = e % k, j = e / k;
-        G[i + (size_t)j * ld] = i >= j ? A[i + (size_t)j * k] : A[j + (size_t)i * k];
-      }
-      if (tid == 0 && attempt == 0) s_shift = T(0);
-      __syncthreads();
-      if (attempt == 1) {
-        T lowest = sizeof(T) == 8 ? T(1e300) : T(3e38);
-        T scale = T(0);
-        for (int i = tid; i < k; i += nt) {
-          T off = 0;
-          for (int j = 0; j < k; ++j)
-            if (j != i) off += fabs(G[i + (size_t)j * ld]);
-          lowest = min(lowest, G[i + (size_t)i * ld] - off);
-          scale = max(scale, fabs(G[i + (size_t)i * ld]) + off);
-        }
-        red_lo[tid] = lowest;
-        red_sc[tid] = scale;
+    const int64_t u0 = rb * run, u1 = u0 + run < n ? u0 + run : n;
+    bool prev_ok = false;
+    for (int64_t u = u0; u < u1; ++u) {
+      T *Gg = MODE == 0 ? Cio + u * (int64_t)k * k : Vout + u * (int64_t)k * k;
+      T *G = SMEM ? Gs : Gg;
+      const bool warm = can_chain && prev_ok;
+      const T *Up = MODE == 0 && u > u0 ? Cio + (u - 1) * (int64_t)k * k : nullptr;  // U of the previous unit
+      if (MODE == 0) {
         __syncthreads();
-        if (tid == 0) {
-          T lo = red_lo[0], sc = red_sc[0];
-          for (int i = 1; i < nt; ++i) {
-            lo = min(lo, red_lo[i]);
-            sc = max(sc, red_sc[i]);
+        if (SMEM)  // Gram kernels deliver the column-major lower triangle: symmetrise while loading
+          for (int e = tid; e < k * k; e += nt) {
+            const int i = e % k, j = e / k;
+            G[i + (size_t)j * ld] = i >= j ? Gg[i + (size_t)j * k] : Gg[j + (size_t)i * k];
           }
-          s_shift = sc * T(1e-3) - min(lo, T(0));
+        if (tid == 0) s_shift = T(0);
+        __syncthreads();
+        if (warm && chain_big) {
+          // S = C U_prev, then C' = U_prev^T S -> G (C: full in shared memory, lower triangle in global)
+          block_gemm_dmma_oop<T>(
+              [&](int i, int l) {
+                return SMEM ? (double)G[i + (size_t)l * ld] : (double)(i >= l ? G[i + (size_t)l * ld] : G[l + (size_t)i * ld]);
+              },
+              [&](int l, int j) { return (double)Up[l + (size_t)j * k]; }, S, k, k);
+          block_gemm_dmma_oop<T>([&](int i, int l) { return (double)Up[l + (size_t)i * k]; },
+                                 [&](int l, int j) { return (double)S[l + (size_t)j * k]; }, G, ld, k);
+        } else if (warm) {
+          // T = C U_prev, then C' = U_prev^T T (both written over G)
+          block_gemm_dmma<T>([&](int i, int l) { return (double)G[i + (size_t)l * ld]; },
+                             [&](int l, int j) { return (l < k && j < k) ? (double)Up[l + (size_t)j * k] : 0.0; }, G, ld, kp);
+          block_gemm_dmma<T>([&](int i, int l) { return (l < k && i < k) ? (double)Up[l + (size_t)i * k] : 0.0; },
+                             [&](int l, int j) { return (double)G[l + (size_t)j * ld]; }, G, ld, kp);
         }
-        __syncthreads();
-        const T sh = s_shift;
-        for (int i = tid; i < k; i += nt) G[i + (size_t)i * ld] += sh;
-        __syncthreads();
-      }
-      if (SMEM ? block_cholesky(G, k, ld) : block_cholesky_panel(G, k, Gs)) break;
-    }
-  }
-
-  // MODE 0 feeds the LETKF weights (1e-10 bar): stop once a sweep saw only |cos| <= 1e-7 and take the
-  // rotation angle in real32.  MODE 1 is the general eigensolver: |cos| <= 1e-9, angle in working precision.
-  const T stop2 = MODE == 0 ? T(1e-14) : (sizeof(T) == 8 ? T(1e-18) : T(1e-9));
-  int sweeps;
-  if (SMEM) {
-    sweeps = block_jacobi_rb<T, RPL, MODE == 0>(G, k, kp, ld, k, nrm, stop2);
-  } else {
-    // the first nres columns stay in shared memory for the sweeps (over the Cholesky panel, now free)
-    for (int e = tid; e < nres * k; e += nt) Gs[e] = G[e];
-    __syncthreads();
-    sweeps = block_jacobi_rb<T, RPL, MODE == 0, true>(G, k, kp, ld, k, nrm, stop2, Gs, k, nres);
-    for (int e = tid; e < nres * k; e += nt) G[e] = Gs[e];
-    __syncthreads();
-  }
-  if (tid == 0 && sweeps_max) atomicMax(sweeps_max, sweeps);
-  if (tid == 0 && sweeps_sum) atomicAdd(sweeps_sum, sweeps);
-
-  // column norms -> eigenvalues; normalise columns -> eigenvectors
-  for (int j = warp; j < k; j += nw) {
-    T *gj = G + (size_t)j * ld;
-    T a = 0;
-    for (int i = lane; i < k; i += 32) a += gj[i] * gj[i];
-    a = warp_sum(a);
-    const T inv = T(1) / sqrt(a);
-    for (int i = lane; i < k; i += 32) gj[i] *= inv;
-    if (lane == 0) vec1[j] = a;  // lambda (+ shift)
-  }
-  __syncthreads();
-
-  if (MODE == 0) {
-    if (warm && chain_big) {
-      // U = U_prev U'
-      block_gemm_dmma_oop<T>([&](int i, int l) { return (double)Up[i + (size_t)l * k]; },
-                             [&](int l, int j) { return (double)G[l + (size_t)j * ld]; }, S, k, k);
-      for (int e = tid; e < k * k; e += nt) G[(e % k) + (size_t)(e / k) * ld] = S[e];
-      __syncthreads();
-    } else if (warm) {
-      // U = U_prev U'
-      block_gemm_dmma<T>([&](int i, int l) { return (i < k && l < k) ? (double)Up[i + (size_t)l * k] : 0.0; },
-                         [&](int l, int j) { return (double)G[l + (size_t)j * ld]; }, G, ld, kp);
-    }
-    {
-      // a unit whose matrix is not finite / not positive must not seed its neighbour
-      int bad = 0;
-      for (int j = tid; j < k; j += nt) bad |= !(vec1[j] > T(0)) || !(vec1[j] < T(1e30));
-      prev_ok = !__syncthreads_or(bad);
-    }
-    // wbar = U diag(1/lam) U^T b   (inverse_matrix + ?gemv + ?symv, eig:37-76, core:651-652)
-    const T *b = bvec + u * (int64_t)k;
-    for (int j = warp; j < k; j += nw) {
-      const T *gj = G + (size_t)j * ld;
-      T a = 0;
-      for (int i = lane; i < k; i += 32) a += gj[i] * b[i];
-      a = warp_sum(a);
-      if (lane == 0) vec2[j] = a / vec1[j];
-    }
-    __syncthreads();
-    for (int i = tid; i < k; i += nt) {
-      T a = 0;
-      for (int j = 0; j < k; ++j) a += G[i + (size_t)j * ld] * vec2[j];
-      wbar[u * (int64_t)k + i] = a;
-      lam[u * (int64_t)k + i] = vec1[i];
-    }
-    if (SMEM)
-      for (int e = tid; e < k * k; e += nt) Gg[e] = G[(e % k) + (size_t)(e / k) * ld];
-  } else {
-    // ascending order like LAPACK: rank by counting
-    const T sh = s_shift;
-    int *rank = reinterpret_cast<int *>(vec2);
-    for (int j = tid; j < k; j += nt) {
-      const T lj = vec1[j];
-      int r = 0;
-      for (int l = 0; l < k; ++l) {
-        const T ll = vec1[l];
-        r += (ll < lj) || (ll == lj && l < j);
-      }
-      rank[j] = r;
-      Wout[u * (int64_t)k + r] = lj - sh;
-    }
-    __syncthreads();
-    if (SMEM) {
-      for (int e = tid; e < k * k; e += nt) {
-        const int i = e % k, j = e / k;
-        Gg[i + (size_t)rank[j] * k] = G[i + (size_t)j * ld];
-      }
-    } else {
-      // in-place column permutation in global memory: every thread owns rows and walks the cycles
-      for (int i = tid; i < k; i += nt) {
-        for (int start = 0; start < k; ++start) {
-          int c = rank[start];
-          bool smallest = true;
-          while (c != start) {
-            if (c < start) {
-              smallest = false;
-              break;
+        // C is SPD by construction; a NaN input propagates
+        if (SMEM)
+          block_cholesky(G, k, ld);
+        else
+          block_cholesky_panel(G, k, Gs);
+      } else {
+        const T *A = Ain + u * (int64_t)k * k;
+        // First try the matrix as it is (an SPD input keeps its full relative accuracy); if a pivot
+        // fails, shift by a Gershgorin bound so that it becomes definite and factor again.
+        for (int attempt = 0; attempt < 2; ++attempt) {
+          __syncthreads();
+          for (int e = tid; e < k * k; e += nt) {  // symmetrise from the lower triangle
+            const int i = e % k, j = e / k;
+            G[i + (size_t)j * ld] = i >= j ? A[i + (size_t)j * k] : A[j + (size_t)i * k];
+          }
+          if (tid == 0 && attempt == 0) s_shift = T(0);
+          __syncthreads();
+          if (attempt == 1) {
+            T lowest = sizeof(T) == 8 ? T(1e300) : T(3e38);
+            T scale = T(0);
+            for (int i = tid; i < k; i += nt) {
+              T off = 0;
+              for (int j = 0; j < k; ++j)
+                if (j != i) off += fabs(G[i + (size_t)j * ld]);
+              lowest = min(lowest, G[i + (size_t)i * ld] - off);
+              scale = max(scale, fabs(G[i + (size_t)i * ld]) + off);
             }
-            c = rank[c];
+            red_lo[tid] = lowest;
+            red_sc[tid] = scale;
+            __syncthreads();
+            if (tid == 0) {
+              T lo = red_lo[0], sc = red_sc[0];
+              for (int i = 1; i < nt; ++i) {
+                lo = min(lo, red_lo[i]);
+                sc = max(sc, red_sc[i]);
+              }
+              s_shift = sc * T(1e-3) - min(lo, T(0));
+            }
+            __syncthreads();
+            const T sh = s_shift;
+            for (int i = tid; i < k; i += nt) G[i + (size_t)i * ld] += sh;
+            __syncthreads();
           }
-          if (!smallest) continue;
-          T carry = G[i + (size_t)start * k];
-          int dst = rank[start];
-          while (dst != start) {
-            const T tmp = G[i + (size_t)dst * k];
-            G[i + (size_t)dst * k] = carry;
-            carry = tmp;
-            dst = rank[dst];
-          }
-          G[i + (size_t)start * k] = carry;
+          if (SMEM ? block_cholesky(G, k, ld) : block_cholesky_panel(G, k, Gs)) break;
         }
       }
-    }
-  }
-  __syncthreads();
-  }  // unit loop
+
+      // MODE 0 feeds the LETKF weights (1e-10 bar): stop once a sweep saw only |cos| <= 1e-7 and take the
+      // rotation angle in real32.  MODE 1 is the general eigensolver: |cos| <= 1e-9, angle in working precision.
+      const T stop2 = MODE == 0 ? T(1e-14) : (sizeof(T) == 8 ? T(1e-18) : T(1e-9));
+      int sweeps;
+      if (SMEM) {
+        sweeps = block_jacobi_rb<T, RPL, MODE == 0>(G, k, kp, ld, k, nrm, stop2);
+      } else {
+        // the first nres columns stay in shared memory for the sweeps (over the Cholesky panel, now free)
+        for (int e = tid; e < nres * k; e += nt) Gs[e] = G[e];
+        __syncthreads();
+        sweeps = block_jacobi_rb<T, RPL, MODE == 0, true>(G, k, kp, ld, k, nrm, stop2, Gs, k, nres);
+        for (int e = tid; e < nres * k; e += nt) G[e] = Gs[e];
+        __syncthreads();
+      }
+      if (tid == 0 && sweeps_max) atomicMax(sweeps_max, sweeps);
+      if (tid == 0 && sweeps_sum) atomicAdd(sweeps_sum, sweeps);
+
+      // column norms -> eigenvalues; normalise columns -> eigenvectors
+      for (int j = warp; j < k; j += nw) {
+        T *gj = G + (size_t)j * ld;
+        T a = 0;
+        for (int i = lane; i < k; i += 32) a += gj[i] * gj[i];
+        a = warp_sum(a);
+        const T inv = T(1) / sqrt(a);
+        for (int i = lane; i < k; i += 32) gj[i] *= inv;
+        if (lane == 0) vec1[j] = a;  // lambda (+ shift)
+      }
+      __syncthreads();
+
+      if (MODE == 0) {
+        if (warm && chain_big) {
+          // U = U_prev U'
+          block_gemm_dmma_oop<T>([&](int i, int l) { return (double)Up[i + (size_t)l * k]; },
+                                 [&](int l, int j) { return (double)G[l + (size_t)j * ld]; }, S, k, k);
+          for (int e = tid; e < k * k; e += nt) G[(e % k) + (size_t)(e / k) * ld] = S[e];
+          __syncthreads();
+        } else if (warm) {
+          // U = U_prev U'
+          block_gemm_dmma<T>([&](int i, int l) { return (i < k && l < k) ? (double)Up[i + (size_t)l * k] : 0.0; },
+                             [&](int l, int j) { return (double)G[l + (size_t)j * ld]; }, G, ld, kp);
+        }
+        {
+          // a unit whose matrix is not finite / not positive must not seed its neighbour
+          int bad = 0;
+          for (int j = tid; j < k; j += nt) bad |= !(vec1[j] > T(0)) || !(vec1[j] < T(1e30));
+          prev_ok = !__syncthreads_or(bad);
+        }
+        // wbar = U diag(1/lam) U^T b   (inverse_matrix + ?gemv + ?symv, eig:37-76, core:651-652)
+        const T *b = bvec + u * (int64_t)k;
+        for (int j = warp; j < k; j += nw) {
+          const T *gj = G + (size_t)j * ld;
+          T a = 0;
+          for (int i = lane; i < k; i += 32) a += gj[i] * b[i];
+          a = warp_sum(a);
+          if (lane == 0) vec2[j] = a / vec1[j];
+        }
+        __syncthreads();
+        for (int i = tid; i < k; i += nt) {
+          T a = 0;
+          for (int j = 0; j < k; ++j) a += G[i + (size_t)j * ld] * vec2[j];
+          wbar[u * (int64_t)k + i] = a;
+          lam[u * (int64_t)k + i] = vec1[i];
+        }
+        if (SMEM)
+          for (int e = tid; e < k * k; e += nt) Gg[e] = G[(e % k) + (size_t)(e / k) * ld];
+      } else {
+        // ascending order like LAPACK: rank by counting
+        const T sh = s_shift;
+        int *rank = reinterpret_cast<int *>(vec2);
+        for (int j = tid; j < k; j += nt) {
+          const T lj = vec1[j];
+          int r = 0;
+          for (int l = 0; l < k; ++l) {
+            const T ll = vec1[l];
+            r += (ll < lj) || (ll == lj && l < j);
+          }
+          rank[j] = r;
+          Wout[u * (int64_t)k + r] = lj - sh;
+        }
+        __syncthreads();
+        if (SMEM) {
+          for (int e = tid; e < k * k; e += nt) {
+            const int i = e % k, j = e / k;
+            Gg[i + (size_t)rank[j] * k] = G[i + (size_t)j * ld];
+          }
+        } else {
+          // in-place column permutation in global memory: every thread owns rows and walks the cycles
+          for (int i = tid; i < k; i += nt) {
+            for (int start = 0; start < k; ++start) {
+              int c = rank[start];
+              bool smallest = true;
+              while (c != start) {
+                if (c < start) {
+                  smallest = false;
+                  break;
+                }
+                c = rank[c];
+              }
+              if (!smallest) continue;
+              T carry = G[i + (size_t)start * k];
+              int dst = rank[start];
+              while (dst != start) {
+                const T tmp = G[i + (size_t)dst * k];
+                G[i + (size_t)dst * k] = carry;
+                carry = tmp;
+                dst = rank[dst];
+              }
+              G[i + (size_t)start * k] = carry;
+            }
+          }
+        }
+      }
+      __syncthreads();
+    }  // unit loop
   }  // run loop
 }
 
