@@ -24,6 +24,30 @@ def test_library_exports_every_declared_symbol():
     assert L.letkf_b200_version() >= 100
 
 
+def test_ctypes_bindings_match_the_header_arity():
+    """Every prototype in include/letkf_b200.h has as many parameters as the ctypes binding in host.py
+    (an ABI drift between the header, the library and the Python mirror shows up here, without a GPU), and
+    the Fortran ISO_C_BINDING module declares an interface for every call the driver shim makes."""
+    L = H.load_library()
+    hdr = open(os.path.join(ROOT, "include", "letkf_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    protos = re.findall(r"\b(letkf_b200_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", hdr, flags=re.S)
+    assert len(protos) >= 20
+    checked = 0
+    for name, args in protos:
+        args = args.strip()
+        n = 0 if args in ("", "void") else args.count(",") + 1
+        fn = getattr(L, name)
+        if fn.argtypes is not None:
+            assert len(fn.argtypes) == n, (name, n, len(fn.argtypes))
+            checked += 1
+    assert checked >= 15
+    f90 = open(os.path.join(ROOT, "cwbnwp_letkf_b200", "fortran", "letkf_b200_mod.f90")).read().lower()
+    for name in ("letkf_b200_init", "letkf_b200_finalize", "letkf_b200_set_obs", "letkf_b200_analyze",
+                 "letkf_b200_last_error"):
+        assert re.search(r'bind\(c,\s*name\s*=\s*"%s"\)' % name, f90), name
+
+
 def test_no_gpu_means_loud_failure():
     import torch
     if torch.cuda.is_available():
