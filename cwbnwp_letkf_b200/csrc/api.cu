@@ -50,6 +50,18 @@ struct letkf_b200_ctx {
   DevBuf<unsigned char> cub_tmp;
   DevBuf<unsigned char> C, b, lam, wbar;  // sized in bytes for the working precision
   std::vector<cudaEvent_t> io_ev;         // chunk-granular host IO: [2*i] upload done, [2*i+1] chunk analysed
+  CtxShared shared;                       // launch counter, eigensolver scratch (bound per call, CtxBind)
+  // FP64 solve = Householder tridiagonalisation + pole expansion of C^(-1/2) (fcn_common.cuh); the
+  // Jacobi eigensolver path stays selectable (LETKF_B200_SOLVER=jacobi) and serves the FP32 build
+  bool use_fcn = true;
+  DevBuf<double> poles;
+};
+
+// binds the context's shared state to the calling thread for one C-ABI call
+struct CtxBind {
+  CtxShared *prev;
+  explicit CtxBind(letkf_b200_ctx *c) : prev(current_ctx_shared()) { current_ctx_shared() = c ? &c->shared : nullptr; }
+  ~CtxBind() { current_ctx_shared() = prev; }
 };
 
 template <typename F>
@@ -62,6 +74,12 @@ static int guarded(F &&f) {
     cudaGetLastError();  // clear a sticky-less error state
     return 1;
   }
+}
+
+template <typename F>
+static int guarded(letkf_b200_ctx *c, F &&f) {
+  CtxBind bind(c);
+  return guarded(std::forward<F>(f));
 }
 
 extern "C" const char *letkf_b200_last_error(void) { return g_last_error.c_str(); }
@@ -84,14 +102,21 @@ extern "C" int letkf_b200_init(letkf_b200_ctx **out, int nmember, int real64, in
     c->device = device;
     const char *fg = getenv("LETKF_B200_GENERIC");
     c->force_generic = fg && fg[0] == '1';
+    const char *sv = getenv("LETKF_B200_SOLVER");
+    c->use_fcn = c->real64 && !(sv && std::string(sv) == "jacobi");
     LK_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     for (auto &ev : c->ev) LK_CUDA(cudaEventCreate(&ev));
+    if (c->use_fcn) {
+      const std::vector<double> &tab = fcn_pole_table_host();
+      c->poles.ensure(tab.size());
+      LK_CUDA(cudaMemcpy(c->poles.p, tab.data(), sizeof(double) * tab.size(), cudaMemcpyHostToDevice));
+    }
     *out = c.release();
   });
 }
 
 extern "C" int letkf_b200_finalize(letkf_b200_ctx *c) {
-  return guarded([&] {
+  return guarded(c, [&] {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
@@ -112,7 +137,7 @@ extern "C" int letkf_b200_finalize(letkf_b200_ctx *c) {
   });
 }
 
-extern "C" int64_t letkf_b200_launch_count(letkf_b200_ctx *) { return launch_counter(); }
+extern "C" int64_t letkf_b200_launch_count(letkf_b200_ctx *c) { return c ? c->shared.launches : 0; }
 extern "C" void *letkf_b200_stream(letkf_b200_ctx *c) { return c ? (void *)c->stream : nullptr; }
 extern "C" int letkf_b200_set_levels(letkf_b200_ctx *c, int nz) {
   if (!c || nz < 1) return 1;
@@ -189,15 +214,15 @@ static void set_obs_impl(letkf_b200_ctx *c, int family, int type, int n, int nva
 extern "C" int letkf_b200_set_obs(letkf_b200_ctx *c, int family, int type, int n, int nvar, const float *xyz,
                                   const float *obs, const float *error, const float *hdxb,
                                   const int32_t *qc) {
-  return guarded([&] { set_obs_impl(c, family, type, n, nvar, xyz, obs, error, hdxb, qc, false); });
+  return guarded(c, [&] { set_obs_impl(c, family, type, n, nvar, xyz, obs, error, hdxb, qc, false); });
 }
 extern "C" int letkf_b200_set_obs_dev(letkf_b200_ctx *c, int family, int type, int n, int nvar,
                                       const float *xyz, const float *obs, const float *error,
                                       const float *hdxb, const int32_t *qc) {
-  return guarded([&] { set_obs_impl(c, family, type, n, nvar, xyz, obs, error, hdxb, qc, true); });
+  return guarded(c, [&] { set_obs_impl(c, family, type, n, nvar, xyz, obs, error, hdxb, qc, true); });
 }
 extern "C" int letkf_b200_clear_obs(letkf_b200_ctx *c) {
-  return guarded([&] {
+  return guarded(c, [&] {
     LK_REQUIRE(c, "null context");
     LK_CUDA(cudaSetDevice(c->device));
     LK_CUDA(cudaStreamSynchronize(c->stream));
@@ -449,7 +474,8 @@ static void run_pipeline(letkf_b200_ctx *c, const letkf_b200_var_config *cfg, in
         const bool fast32 = k == 32 && !c->force_generic;  // warp-per-unit register kernels
         // k = 32 FP64 with one transform per unit and no parity dump: the transform runs in the
         // eigensolver's epilogue and U never leaves the registers
-        const bool fuse = fast32 && sizeof(T) == 8 && nz == 1 && co.transform && nfields > 0 && !co.wbar &&
+        const bool use_fcn = c->use_fcn && sizeof(T) == 8;
+        const bool fuse = !use_fcn && fast32 && sizeof(T) == 8 && nz == 1 && co.transform && nfields > 0 && !co.wbar &&
                           !co.Wa && eig32_can_fuse();
         Xform32Args xargs{c->unit_pt.p, c->nanflag.p, npts, c0, nfields, d_var, cfg->use_rtpp, cfg->rtpp_alpha,
                           cfg->use_rtps, cfg->rtps_alpha, co.xa_raw};
@@ -475,6 +501,38 @@ static void run_pipeline(letkf_b200_ctx *c, const letkf_b200_var_config *cfg, in
         else
           launch_gram<T>(s, tv, k, nunits, c->unit_pt.p, mu, C, b, c->nanflag.p);
         LK_CUDA(cudaEventRecord(c->ev[4], s));
+        if (use_fcn) {
+          // tridiagonalisation + pole expansion: solve, transform of every level / field and the parity dump
+          // in one kernel (fcn_common.cuh); nothing but C, b and the field columns is read or written
+          FcnArgs fa;
+          fa.k = k;
+          fa.nunits = nunits;
+          fa.C = reinterpret_cast<double *>(C);
+          fa.bvec = reinterpret_cast<const double *>(b);
+          fa.unit_pt = c->unit_pt.p;
+          fa.nanflag = c->nanflag.p;
+          fa.mu = (double)mu;
+          fa.poles = c->poles.p;
+          fa.npts_total = npts;
+          fa.pt_base = c0;
+          fa.level_stride = nsearch;
+          fa.nz = nz;
+          fa.nfields = nfields;
+          fa.var = (co.transform && nfields > 0) ? d_var : nullptr;
+          fa.use_rtpp = cfg->use_rtpp;
+          fa.rtpp_alpha = cfg->rtpp_alpha;
+          fa.use_rtps = cfg->use_rtps;
+          fa.rtps_alpha = cfg->rtps_alpha;
+          fa.xa_raw = co.xa_raw;
+          fa.wbar_out = co.wbar ? co.wbar + c0 * k : nullptr;
+          fa.Wa_out = co.Wa ? co.Wa + c0 * (int64_t)k * k : nullptr;
+          if (fast32)
+            launch_fcn32_solve(s, fa);
+          else
+            launch_fcn_solve(s, fa);
+          launch_counter()++;
+          LK_CUDA(cudaEventRecord(c->ev[5], s));
+        } else {
         if (fast32)
           launch_eig32_solve<T>(s, nunits, C, b, lam, wbar, c->counters.p + 1, fuse ? &xargs : nullptr);
         else
@@ -498,6 +556,7 @@ static void run_pipeline(letkf_b200_ctx *c, const letkf_b200_var_config *cfg, in
               launch_transform<T>(s, k, nunits, c->unit_pt.p, npts, base, C, lam, wbar, c->nanflag.p, nfields, d_var,
                                   cfg->use_rtpp, cfg->rtpp_alpha, cfg->use_rtps, cfg->rtps_alpha, co.xa_raw);
           }
+        }
         }
         }
         LK_CUDA(cudaEventRecord(c->ev[6], s));
@@ -556,7 +615,7 @@ static void analyze_dev_impl(letkf_b200_ctx *c, const letkf_b200_var_config *cfg
 
 extern "C" int letkf_b200_analyze_dev(letkf_b200_ctx *c, const letkf_b200_var_config *cfg, int64_t npts,
                                       const float *xyz, int nfields, float *var, letkf_b200_stats *st) {
-  return guarded([&] { analyze_dev_impl(c, cfg, npts, xyz, nfields, var, st); });
+  return guarded(c, [&] { analyze_dev_impl(c, cfg, npts, xyz, nfields, var, st); });
 }
 
 static void ensure_copy_streams(letkf_b200_ctx *c) {
@@ -579,7 +638,7 @@ static void ensure_copy_streams(letkf_b200_ctx *c) {
 // are independent, so slabbing does not change results.
 extern "C" int letkf_b200_analyze(letkf_b200_ctx *c, const letkf_b200_var_config *cfg, int64_t npts,
                                   const float *xyz, int nfields, float *var, letkf_b200_stats *st) {
-  return guarded([&] {
+  return guarded(c, [&] {
     LK_REQUIRE(c && cfg, "null context / config");
     LK_REQUIRE(npts >= 0 && nfields >= 0, "negative size");
     LK_REQUIRE(npts == 0 || (xyz && (nfields == 0 || var)), "null array");
@@ -668,7 +727,7 @@ extern "C" int letkf_b200_analyze(letkf_b200_ctx *c, const letkf_b200_var_config
 }
 
 extern "C" int letkf_b200_tune_q_dev(letkf_b200_ctx *c, int64_t npts, float *var) {
-  return guarded([&] {
+  return guarded(c, [&] {
     LK_REQUIRE(c && (npts == 0 || var), "null argument");
     LK_CUDA(cudaSetDevice(c->device));
     launch_tune_q(c->stream, c->k, npts, var);
@@ -676,7 +735,7 @@ extern "C" int letkf_b200_tune_q_dev(letkf_b200_ctx *c, int64_t npts, float *var
   });
 }
 extern "C" int letkf_b200_tune_q(letkf_b200_ctx *c, int64_t npts, float *var) {
-  return guarded([&] {
+  return guarded(c, [&] {
     LK_REQUIRE(c && (npts == 0 || var), "null argument");
     LK_CUDA(cudaSetDevice(c->device));
     const size_t nv = (size_t)npts * c->k;
@@ -692,7 +751,7 @@ extern "C" int letkf_b200_tune_q(letkf_b200_ctx *c, int64_t npts, float *var) {
 extern "C" int letkf_b200_search(letkf_b200_ctx *c, const letkf_b200_var_config *cfg, int64_t npts,
                                  const float *xyz, int32_t *ntrees, int32_t *family, int32_t *type,
                                  int32_t *stride, int32_t *count, int32_t *idx, float *r2) {
-  return guarded([&] {
+  return guarded(c, [&] {
     LK_REQUIRE(c && cfg && ntrees, "null argument");
     LK_CUDA(cudaSetDevice(c->device));
     std::vector<ActiveTree> act = prepare_trees(c, cfg);
@@ -732,7 +791,7 @@ extern "C" int letkf_b200_search(letkf_b200_ctx *c, const letkf_b200_var_config 
 
 extern "C" int letkf_b200_yoyb(letkf_b200_ctx *c, const letkf_b200_var_config *cfg, int64_t npts,
                                const float *xyz, int64_t *row_offset, float *yo, float *yb) {
-  return guarded([&] {
+  return guarded(c, [&] {
     LK_REQUIRE(c && cfg && row_offset && (npts == 0 || xyz), "null argument");
     LK_CUDA(cudaSetDevice(c->device));
     cudaStream_t s = c->stream;
@@ -774,7 +833,7 @@ extern "C" int letkf_b200_yoyb(letkf_b200_ctx *c, const letkf_b200_var_config *c
 extern "C" int letkf_b200_weights(letkf_b200_ctx *c, const letkf_b200_var_config *cfg, int64_t npts,
                                   const float *xyz, const float *xb, int32_t *p, double *wbar, double *Wa,
                                   double *xa_raw) {
-  return guarded([&] {
+  return guarded(c, [&] {
     LK_REQUIRE(c && cfg && (npts == 0 || xyz), "null argument");
     LK_REQUIRE(!xa_raw || xb, "xa_raw needs xb");
     LK_CUDA(cudaSetDevice(c->device));
@@ -841,7 +900,7 @@ static void syevd_dev(letkf_b200_ctx *c, int k, int64_t batch, const void *A, vo
 
 extern "C" int letkf_b200_syevd_batched_dev(letkf_b200_ctx *c, int k, int64_t batch, int real64, const void *A,
                                             void *W, void *V, int32_t *sweeps) {
-  return guarded([&] {
+  return guarded(c, [&] {
     LK_REQUIRE(c && (batch == 0 || (A && W && V)), "null argument");
     LK_REQUIRE(A != V, "A and V must not alias");
     LK_CUDA(cudaSetDevice(c->device));
@@ -854,7 +913,7 @@ extern "C" int letkf_b200_syevd_batched_dev(letkf_b200_ctx *c, int k, int64_t ba
 
 extern "C" int letkf_b200_syevd_batched(letkf_b200_ctx *c, int k, int64_t batch, int real64, const void *A,
                                         void *W, void *V, int32_t *sweeps) {
-  return guarded([&] {
+  return guarded(c, [&] {
     LK_REQUIRE(c && (batch == 0 || (A && W && V)), "null argument");
     LK_CUDA(cudaSetDevice(c->device));
     const size_t ts = real64 ? 8 : 4;
@@ -875,7 +934,7 @@ extern "C" int letkf_b200_syevd_batched(letkf_b200_ctx *c, int k, int64_t batch,
 }
 
 extern "C" int letkf_b200_fma_peak(letkf_b200_ctx *c, int kind, double *tflops) {
-  return guarded([&] {
+  return guarded(c, [&] {
     LK_REQUIRE(c && tflops, "null argument");
     LK_CUDA(cudaSetDevice(c->device));
     *tflops = run_fma_peak(c->stream, kind);

@@ -672,11 +672,12 @@ __global__ void __launch_bounds__(RPL >= 5 ? 256 : 512)
   }  // run loop
 }
 
-// warm-start scratch of the persistent large-k kernel: grow-only, lives as long as the library
+// warm-start scratch of the persistent large-k kernel: grow-only, owned by the calling context
 static unsigned char *eig_scratch(size_t bytes) {
-  static DevBuf<unsigned char> buf;
-  buf.ensure(bytes);
-  return buf.p;
+  CtxShared *c = current_ctx_shared();
+  LK_REQUIRE(c != nullptr, "eigensolver launched outside a library context");
+  c->eig_scratch.ensure(bytes);
+  return c->eig_scratch.p;
 }
 
 template <typename T, int MODE, int RPL>

@@ -7,9 +7,14 @@
 
 namespace lk {
 
+CtxShared *&current_ctx_shared() {
+  static thread_local CtxShared *cur = nullptr;
+  return cur;
+}
 int64_t &launch_counter() {
-  static int64_t c = 0;
-  return c;
+  static thread_local int64_t unbound = 0;  // launches outside any context (none in practice)
+  CtxShared *c = current_ctx_shared();
+  return c ? c->launches : unbound;
 }
 
 // ---- once per set_obs: mean, perturbations, spread, any(qc>=0) -------------------------------

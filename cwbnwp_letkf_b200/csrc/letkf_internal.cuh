@@ -200,6 +200,40 @@ template <typename T>
 void launch_weights_dump32(cudaStream_t s, int64_t nunits, const int32_t *unit_pt, const T *U, const T *lam,
                            const T *wbar, double *wbar_out, double *Wa_out);
 
+// ---- matrix-function solver (fcn_common.cuh): FP64 replacement of eigen + transform (+ weights dump) ----
+struct FcnArgs {
+  int k;
+  int64_t nunits;
+  double *C;            // [nunits][k][k]: lower triangle (column-major) or full symmetric; overwritten
+  const double *bvec;   // [nunits][k]
+  const int32_t *unit_pt, *nanflag;
+  double mu;            // (k-1)/rho: lower bound of the spectrum
+  const double *poles;  // device copy of the pole table
+  // transform: var == nullptr skips it.  Point of (unit, level) = pt_base + level*level_stride + unit_pt[unit]
+  int64_t npts_total, pt_base, level_stride;
+  int nz, nfields;
+  float *var;
+  int use_rtpp;
+  float rtpp_alpha;
+  int use_rtps;
+  float rtps_alpha;
+  double *xa_raw;
+  // parity dump (either may be null), indexed by unit_pt
+  double *wbar_out, *Wa_out;
+};
+void launch_fcn_solve(cudaStream_t s, const FcnArgs &a);     // CTA per unit, any k
+void launch_fcn32_solve(cudaStream_t s, const FcnArgs &a);   // warp per unit, k = 32
+const std::vector<double> &fcn_pole_table_host();
+
+// Per-context state the kernel launchers need (launch count, the warm-start scratch of the large-k
+// Jacobi kernel).  Every C-ABI entry point binds its context to the calling thread for the duration of
+// the call (CtxBind in api.cu); nothing is process-global, so contexts on different devices / threads do
+// not share or race on it.
+struct CtxShared {
+  int64_t launches = 0;
+  DevBuf<unsigned char> eig_scratch;
+};
+CtxShared *&current_ctx_shared();
 int64_t &launch_counter();
 
 }  // namespace lk

@@ -61,7 +61,7 @@ EXPORTS = ["letkf_b200_init", "letkf_b200_finalize", "letkf_b200_last_error", "l
            "letkf_b200_yoyb", "letkf_b200_weights", "letkf_b200_syevd_batched",
            "letkf_b200_syevd_batched_dev", "letkf_b200_fma_peak", "letkf_b200_launch_count",
            "letkf_b200_stream", "letkf_b200_set_chunk", "letkf_b200_set_levels",
-           "letkf_b200_selftest_host_search"]
+           "letkf_b200_selftest_host_search", "letkf_b200_selftest_pole_table"]
 
 
 def library_path() -> str:
@@ -103,6 +103,7 @@ def load_library():
     L.letkf_b200_set_levels.argtypes = [vp, i32]
     L.letkf_b200_selftest_host_search.argtypes = [i32, vp, ctypes.c_float, ctypes.c_float, i64, vp, i32, vp,
                                                   vp, vp, vp, vp]
+    L.letkf_b200_selftest_pole_table.argtypes = [vp, i32]
     _LIB = L
     return L
 

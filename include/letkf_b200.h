@@ -181,6 +181,13 @@ int letkf_b200_selftest_host_search(int n, const float *obs_xyz, float hclr, flo
                                     const float *xyz_grid, int max_lz_pts, int32_t *ind_out,
                                     int32_t *nnodes_out, int32_t *count, int32_t *idx, float *r2);
 
+/* Host-only self-test, no GPU needed and NOT part of any product path: copies the pole table of the
+ * FP64 solve (C^(-1/2) ~ sqrt(a) sum_j c_j (C + a beta_j)^-1 on a spectrum inside [a, a 2^q]; layout
+ * [q][0][j] = c_j, [q][1][j] = beta_j, q = 0..40, j = 0..31) into out[0..cap) and returns its length in
+ * doubles (-1 on failure).  It replaces nothing in the reference: module_eigen.f90:37-108 obtains the same
+ * functions of C from ?syevd.  The CPU test tier checks the table against x^(-1/2). */
+int letkf_b200_selftest_pole_table(double *out, int cap);
+
 /* number of kernels this library launched since init (bench.py's gpu_launches) */
 int64_t letkf_b200_launch_count(letkf_b200_ctx *ctx);
 /* stream the library launches on (cudaStream_t), for CUDA-event timing by the caller */
