@@ -306,23 +306,24 @@ __global__ void __launch_bounds__(512)
   const bool dump = a.wbar_out != nullptr || a.Wa_out != nullptr;
   const int nfv = a.var ? a.nz * a.nfields : 0;
   // list: [b][fields ...][pad so that wbar is not in the first batch][wbar][unit vectors]
-  const int i_wbar = dump ? ((1 + nfv) > FCN_NVW ? (1 + nfv) : FCN_NVW) : -1;
+  const int nvb = nw < FCN_NVW ? nw : FCN_NVW;  // vectors per batch: one warp each
+  const int i_wbar = dump ? ((1 + nfv) > nvb ? (1 + nfv) : nvb) : -1;
   const int nvec = dump ? i_wbar + 1 + (a.Wa_out ? k : 0) : 1 + nfv;
   const bool isnan_unit = a.nanflag[unit] != 0;
   const int64_t upt = a.unit_pt[unit];
   const float ninv = LK_DIV(1.0f, (float)k);
   const double sk = sqrt((double)(k - 1));  // core:666/668
   const int slot = nw - 1 - warp;           // vector slot of this warp (warp 0 last)
-  double *zb = wscr + (size_t)(slot < FCN_NVW ? slot : 0) * wscr_len;
+  double *zb = wscr + (size_t)(slot < nvb ? slot : 0) * wscr_len;
   double *xp = zb + kp;
   float *xb32 = reinterpret_cast<float *>(xp + kp);
   float *xa32 = xb32 + kp;
   double *ck = xp + 2 * kp;
 
-  for (int v0 = 0; v0 < nvec; v0 += FCN_NVW) {
+  for (int v0 = 0; v0 < nvec; v0 += nvb) {
     const int vi = v0 + slot;
     int kind = VK_NONE, sub = 0;
-    if (slot < FCN_NVW && vi < nvec) {
+    if (slot < nvb && vi < nvec) {
       if (vi == 0) kind = VK_B;
       else if (vi <= nfv) { kind = VK_FIELD; sub = vi - 1; }
       else if (vi == i_wbar) kind = VK_WBAR;

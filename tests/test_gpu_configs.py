@@ -1,0 +1,268 @@
+"""GPU tier: parity at the BASELINE.json configurations themselves (not only on the tiny scenario).
+
+  S   100x100x30, k = 32, ~10^4 GTS values: EVERY grid point against the oracle, both weight functions
+      (SURVEY 8(d) "S"; module_letkf_core.f90:209-240 run as one rank);
+  M   450x450x50, k = 32, ~10^6 radar + GTS: 2 000 random points -- lists, yo/Yb rows, weights, field;
+  L   the same observation density with 256 (and 96) members, p > k (~900 rows): 200 points;
+  3D  every active type localised in 3-D (vclr > 0), max_lz_pts 300, k = 64 (README TODO);
+  plus member counts that are not multiples of 4 with p > k, and two contexts alive at once.
+The measured errors are written to gpurun_out/parity_configs.json (when that directory exists) so that the
+numbers, not only pass/fail, are on record.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from cwbnwp_letkf_b200 import config as C
+from cwbnwp_letkf_b200 import host as H
+from cwbnwp_letkf_b200 import synthetic as S
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+TOL64 = 1e-10
+NCPU = max(1, min(32, os.cpu_count() or 1))
+
+
+def _record(name, **vals):
+    d = os.path.join(ROOT, "gpurun_out")
+    if not os.path.isdir(d):
+        return
+    path = os.path.join(d, "parity_configs.json")
+    try:
+        cur = json.load(open(path))
+    except Exception:
+        cur = {}
+    cur[name] = {k: (float(v) if isinstance(v, (float, np.floating)) else int(v) if isinstance(v, (int, np.integer)) else v)
+                 for k, v in vals.items()}
+    with open(path, "w") as f:
+        json.dump(cur, f, indent=1, sort_keys=True)
+
+
+def _engines(sc, real64=True):
+    eng = H.LetkfB200(sc.k, real64)
+    orc = O.Oracle(sc.k, real64)
+    for o in sc.obs.values():
+        eng.set_obs(o)
+        orc.set_obs(o)
+    return eng, orc
+
+
+def _relerr(a, b):
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+
+
+def _bits_equal(a, b):
+    na, nb = np.isnan(a), np.isnan(b)
+    return np.array_equal(na, nb) and np.array_equal(a[~na].view(np.int32), b[~nb].view(np.int32))
+
+
+def _point_parity(eng, orc, cfg, xyz, xb, check_lists=True):
+    """Lists (order + r2 bit-exact), yo/Yb rows (bit-exact), wbar / Wa / pre-cast analysis (1e-10) at the
+    points xyz[(n,3)]; returns the worst errors."""
+    n = xyz.shape[0]
+    lists = eng.get_lz(cfg, xyz) if check_lists else None
+    off, yo, yb = eng.letkf_yoyb(cfg, xyz)
+    p, wbar, Wa, raw = eng.letkf_weights(cfg, xyz, xb)
+    ntrees = orc.build_tree(cfg)
+    inflat = np.float32(eng.k - 1) / np.float32(cfg.multi_infl)
+    worst = dict(wbar=0.0, Wa=0.0, raw=0.0)
+    rows = analysed = 0
+    for i in range(n):
+        if check_lists:
+            ref = orc.get_lz(xyz[i])
+            assert len(ref) == ntrees == len(lists)
+            for t, (fam, typ, idx, r2) in enumerate(ref):
+                gf, gt, cnt, gidx, gr2 = lists[t]
+                assert (gf, gt) == (fam, typ) and cnt[i] == len(idx), (i, t)
+                assert np.array_equal(gidx[i, :cnt[i]], idx), (i, t)
+                assert np.array_equal(gr2[i, :cnt[i]].view(np.int32), r2.view(np.int32)), (i, t)
+        ryo, ryb = orc.letkf_yoyb(xyz[i])
+        a, b = off[i], off[i + 1]
+        assert b - a == len(ryo) == p[i], (i, b - a, len(ryo), p[i])
+        if len(ryo) == 0:
+            assert not wbar[i].any() and not Wa[i].any()
+            continue
+        assert _bits_equal(yo[a:b], ryo) and _bits_equal(yb[a:b], ryb), i
+        _, rw, rWa, rraw = orc.letkf_solve(xb[:, i], ryo, ryb, inflat)
+        if not np.isfinite(rw).all():
+            continue  # Gaspari-Cohn NaN rows: covered by the NaN-site test below
+        worst["wbar"] = max(worst["wbar"], _relerr(wbar[i], rw))
+        worst["Wa"] = max(worst["Wa"], _relerr(Wa[i], rWa))
+        worst["raw"] = max(worst["raw"], _relerr(raw[i], rraw))
+        rows += len(ryo)
+        analysed += 1
+    orc.destroy_tree()
+    assert worst["wbar"] < TOL64 and worst["Wa"] < TOL64 and worst["raw"] < TOL64, worst
+    return worst, analysed, rows
+
+
+def _field_parity(eng, orc, cfg, xyz, f, nthreads=NCPU):
+    ref = f.copy()
+    npo, rows = orc.analyze(cfg, xyz, ref, nthreads=nthreads)
+    got = f.copy()
+    st = eng.analyze(cfg, xyz, got)
+    assert st.npts == xyz.shape[0] and st.npts_analysed == npo and st.rows == rows, (st.as_dict(), npo, rows)
+    assert np.array_equal(np.isnan(got), np.isnan(ref))
+    ok = ~np.isnan(ref)
+    changed = (ref != f).any(0)
+    assert np.array_equal(got[:, ~changed], f[:, ~changed])  # points without local obs: bit-identical
+    scale = np.abs(ref[ok]).max()
+    err = np.abs(got[ok] - ref[ok]).max() / scale
+    same = float((got[ok] == ref[ok]).mean())
+    assert err <= 5e-7, err
+    return err, same, npo, rows
+
+
+# ------------------------------------------------------------------------------------------- S
+@pytest.mark.parametrize("wf", [0, 1])
+def test_config_S_every_point(wf):
+    sc, rng = S.scenario_S()
+    cfg = C.sample_namelist("T", use_radar=False, weight_function=wf)
+    eng, orc = _engines(sc)
+    f = S.make_field(rng, sc.k, sc.xyz_grid, 280.0, 5.0, 1.0)
+    err, same, npo, rows = _field_parity(eng, orc, cfg, sc.xyz_grid, f)
+    assert npo > 0.5 * sc.npts
+    # lists / rows / weights on a random subset (the per-point oracle calls are Python-bound)
+    pts = np.sort(rng.choice(sc.npts, 600, replace=False))
+    worst, analysed, prow = _point_parity(eng, orc, cfg, sc.xyz_grid[pts], np.ascontiguousarray(f[:, pts]))
+    _record("S_wf%d" % wf, points=sc.npts, analysed=npo, rows=rows, field_max_rel=err, field_bit_identical=same,
+            sample=len(pts), **{"max_rel_" + k: v for k, v in worst.items()})
+    eng.finalize()
+
+
+# ------------------------------------------------------------------------------------------- M
+def test_config_M_sampled_points_k32():
+    sc, rng = S.scenario_M(k=32)
+    eng, orc = _engines(sc)
+    out = {}
+    for var, npick in (("T", 2000), ("QRAIN", 500)):
+        cfg = C.sample_namelist(var)
+        pts = np.sort(rng.choice(sc.npts, npick, replace=False))
+        xyz = np.ascontiguousarray(sc.xyz_grid[pts])
+        f = S.make_field(rng, sc.k, xyz, 280.0, 5.0, 1.0)
+        worst, analysed, rows = _point_parity(eng, orc, cfg, xyz, f)
+        err, same, npo, frows = _field_parity(eng, orc, cfg, xyz, f)
+        assert analysed > 0.5 * npick and rows > 100 * analysed
+        out[var] = dict(points=npick, analysed=analysed, rows_per_point=rows / max(analysed, 1), field_max_rel=err,
+                        field_bit_identical=same, **{"max_rel_" + k: v for k, v in worst.items()})
+    _record("M_k32", **{v + "_" + k: x for v, d in out.items() for k, x in d.items()})
+    eng.finalize()
+
+
+# ------------------------------------------------------------------------------------------- L
+@pytest.mark.parametrize("k", [96, 256])
+def test_config_L_observation_density(k):
+    """Config M's observation density (8 radar discs, 6e5 dBZ + 4e5 Vr on 900 km x 900 km) on a 300 km sub-domain
+    so that the member-slowest hdxb stays small on the host: p ~ 900 > k, the regime of the benchmark."""
+    nx = ny = 150
+    rng = np.random.default_rng(20261020 + k)
+    sc = S.Scenario("Lsub", nx, ny, 50, k, 2000.0, S.make_grid(nx, ny, 50, 2000.0))
+    S.add_gts(sc, rng, n_synop=133, n_metar=44, n_ships=11, n_sound=3)
+    S.add_radar(sc, rng, 66667, 44444, n_sites=8, radius=150e3)
+    eng, orc = _engines(sc)
+    cfg = C.sample_namelist("T")
+    pts = np.sort(rng.choice(sc.npts, 200, replace=False))
+    xyz = np.ascontiguousarray(sc.xyz_grid[pts])
+    f = S.make_field(rng, k, xyz, 280.0, 5.0, 1.0)
+    worst, analysed, rows = _point_parity(eng, orc, cfg, xyz, f)
+    err, same, npo, frows = _field_parity(eng, orc, cfg, xyz, f, nthreads=min(NCPU, 8))
+    assert analysed > 150 and rows / analysed > k, (analysed, rows)
+    _record("L_k%d" % k, points=len(pts), analysed=analysed, rows_per_point=rows / analysed, field_max_rel=err,
+            field_bit_identical=same, **{"max_rel_" + kk: v for kk, v in worst.items()})
+    eng.finalize()
+
+
+# ------------------------------------------------------------------------------------------- 3D
+def test_config_3D_all_types_vertical_localisation():
+    """BASELINE config 4: every active type has vclr > 0, max_lz_pts 300, k = 64, dense radar."""
+    k = 64
+    rng = np.random.default_rng(20261021)
+    sc = S.Scenario("3D", 40, 40, 20, k, 2000.0, S.make_grid(40, 40, 20, 2000.0))
+    S.add_gts(sc, rng, n_synop=60, n_metar=30, n_ships=10, n_sound=4, n_lev=20)
+    S.add_radar(sc, rng, 40000, 30000, n_sites=2, radius=30e3)
+    cfg = C.sample_namelist("T")
+    for t in cfg.types:
+        if t.use_it and t.hclr > 0:
+            t.vclr = t.vclr if t.vclr > 0 else 3.0
+            t.max_lz_pts = 300
+    eng, orc = _engines(sc)
+    f = S.make_field(rng, k, sc.xyz_grid, 280.0, 5.0, 1.0)
+    err, same, npo, rows = _field_parity(eng, orc, cfg, sc.xyz_grid, f)
+    pts = np.sort(rng.choice(sc.npts, 150, replace=False))
+    worst, analysed, prow = _point_parity(eng, orc, cfg, np.ascontiguousarray(sc.xyz_grid[pts]),
+                                          np.ascontiguousarray(f[:, pts]))
+    assert npo > 0.5 * sc.npts
+    _record("3D_k64", points=sc.npts, analysed=npo, rows_per_point=rows / npo, field_max_rel=err,
+            field_bit_identical=same, **{"max_rel_" + kk: v for kk, v in worst.items()})
+    eng.finalize()
+
+
+# ------------------------------------------------------------------------------------------- odd member counts
+@pytest.mark.parametrize("k", [30, 50, 99])
+def test_member_counts_not_multiple_of_4_with_many_rows(k):
+    """k % 4 != 0 takes gram_dmma_kernel (no TMA row gather); radar-dense points give p >> k, several row
+    batches and super-blocks."""
+    sc, rng = S.scenario_tiny(k=k, n_dbz=3000, n_vr=2500)
+    cfg = C.sample_namelist("T")
+    eng, orc = _engines(sc)
+    f = S.make_field(rng, k, sc.xyz_grid, 280.0, 5.0, 1.0)
+    err, same, npo, rows = _field_parity(eng, orc, cfg, sc.xyz_grid, f)
+    pts = np.sort(rng.choice(sc.npts, 80, replace=False))
+    worst, analysed, prow = _point_parity(eng, orc, cfg, np.ascontiguousarray(sc.xyz_grid[pts]),
+                                          np.ascontiguousarray(f[:, pts]))
+    assert prow / max(analysed, 1) > k
+    _record("odd_k%d" % k, analysed=npo, rows_per_point=rows / max(npo, 1), field_max_rel=err,
+            **{"max_rel_" + kk: v for kk, v in worst.items()})
+    eng.finalize()
+
+
+# ------------------------------------------------------------------------------------------- solver cross-check
+@pytest.mark.parametrize("k", [32, 64, 160, 256])
+def test_jacobi_and_matrix_function_solvers_agree(k, monkeypatch):
+    """The eigendecomposition path (Cholesky + one-sided Jacobi, LETKF_B200_SOLVER=jacobi) and the default
+    tridiagonalisation + pole-expansion path compute the same functions of C."""
+    sc, rng = S.scenario_tiny(k=k, nx=8, ny=5, nz=4)
+    cfg = C.sample_namelist("T")
+    xb = S.make_field(rng, k, sc.xyz_grid, 280.0, 5.0, 1.0)
+    res = []
+    for solver in ("fcn", "jacobi"):
+        monkeypatch.setenv("LETKF_B200_SOLVER", solver)
+        eng = H.LetkfB200(k, True)
+        for o in sc.obs.values():
+            eng.set_obs(o)
+        res.append(eng.letkf_weights(cfg, sc.xyz_grid, xb))
+        eng.finalize()
+    (p0, w0, W0, r0), (p1, w1, W1, r1) = res
+    assert np.array_equal(p0, p1) and (p0 > 0).sum() > 10
+    assert _relerr(w0, w1) < 1e-11 and _relerr(W0, W1) < 1e-11 and _relerr(r0, r1) < 1e-12
+
+
+def test_two_contexts_do_not_share_state(monkeypatch):
+    """Two library contexts alive at once (the Jacobi path at k = 192 uses a per-context scratch buffer; the
+    launch counters are per context)."""
+    monkeypatch.setenv("LETKF_B200_SOLVER", "jacobi")
+    k = 192
+    sc, rng = S.scenario_tiny(k=k, nx=8, ny=5, nz=4)
+    cfg = C.sample_namelist("T")
+    xb = S.make_field(rng, k, sc.xyz_grid, 280.0, 5.0, 1.0)
+    a, b = H.LetkfB200(k, True), H.LetkfB200(k, True)
+    for o in sc.obs.values():
+        a.set_obs(o)
+    na0, nb0 = a.launch_count, b.launch_count
+    assert na0 > 0 and nb0 == 0
+    for o in sc.obs.values():
+        b.set_obs(o)
+    na0, nb0 = a.launch_count, b.launch_count
+    assert na0 == nb0
+    ra = a.letkf_weights(cfg, sc.xyz_grid, xb)
+    rb = b.letkf_weights(cfg, sc.xyz_grid, xb)
+    ra2 = a.letkf_weights(cfg, sc.xyz_grid, xb)
+    for x, y, z in zip(ra, rb, ra2):
+        assert np.array_equal(x, y) and np.array_equal(x, z)
+    assert a.launch_count - na0 == 2 * (b.launch_count - nb0)
+    a.finalize()
+    b.finalize()
