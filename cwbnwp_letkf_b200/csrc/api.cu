@@ -465,7 +465,7 @@ static void run_pipeline(letkf_b200_ctx *c, const letkf_b200_var_config *cfg, in
       if (co.p) LK_CUDA(cudaMemcpyAsync(co.p + c0, c->p.p, sizeof(int32_t) * nq, cudaMemcpyDeviceToDevice, s));
       if (nunits > 0) {
         if (host_io) LK_CUDA(cudaStreamWaitEvent(s, c->io_ev[2 * ci], 0));  // this chunk's fields are in HBM
-        c->C.ensure((size_t)nunits * k * k * sizeof(T));
+        c->C.ensure((size_t)nunits * k * k * sizeof(T) + 4096);  // the solve may read (and discard) up to 127 rows past a column
         c->b.ensure((size_t)nunits * k * sizeof(T));
         c->lam.ensure((size_t)nunits * k * sizeof(T));
         c->wbar.ensure((size_t)nunits * k * sizeof(T));

@@ -68,14 +68,27 @@ __device__ __forceinline__ void treduce16(double (&v)[16], int lane) {
   v[0] += __shfl_xor_sync(FULLF, v[0], 1);
 }
 
+// 1/x for a pivot: MUFU seed + two Newton steps (~1 ulp; the IEEE divide is a ~25-instruction dependent
+// chain, and there are k of them in sequence per pole).  Pivots are >= mu > 0 and far inside the real32
+// range of the seed; NaN propagates.
+__device__ __forceinline__ double fcn_rcp(double x) {
+  float s;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"((float)x));
+  double r = (double)s;
+  double e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-x, r, 1.0);
+  return fma(r, e, r);
+}
+
 // Reciprocal LDL^T pivots of T + beta I for this lane's pole: rp[i*32 + lane], i = 0..k-1 (one warp).
 __device__ __forceinline__ void pole_pivots(int k, const double *d, const double *e, double beta, double *rp,
                                             int lane) {
-  double rprev = 1.0 / (d[0] + beta);
+  double rprev = fcn_rcp(d[0] + beta);
   rp[lane] = rprev;
   for (int i = 1; i < k; ++i) {
     const double l = e[i - 1] * rprev;
-    rprev = 1.0 / ((d[i] + beta) - l * e[i - 1]);
+    rprev = fcn_rcp((d[i] + beta) - l * e[i - 1]);
     rp[i * 32 + lane] = rprev;
   }
 }

@@ -19,54 +19,123 @@ namespace lk {
 namespace {
 
 constexpr int FCN_NB = 16;    // panel width
-constexpr int FCN_NVW = 4;    // vectors in flight (one warp each)
+constexpr int FCN_NVW = 2;    // vectors in flight (one warp each): b and one field column is the common case
 
 // trailing update A[r][l] -= sum_t V[t][r] W[t][l] + W[t][r] V[t][l] for r, l in [s, k): one warp per
 // (group of 32*RT rows, 4 columns); a thread owns rows R0 + lane + 32 a so that every load is coalesced /
-// conflict free.  V, W: [t][kv] in shared memory (zero beyond k).
-template <int RT>
-__device__ __forceinline__ void trailing_update(double *A, int ld, int k, int s, int pb, const double *V,
+// conflict free.  V, W: [t][kv] in shared memory (zero beyond k).  Interior tiles take the unguarded path.
+template <int RT, typename AP>
+__device__ __forceinline__ void trailing_update(AP A, int ld, int k, int s, int pb, const double *V,
                                                 const double *W, int kv, int warp, int lane, int nw) {
   const int nt = k - s;
-  const int nrg = (nt + 32 * RT - 1) / (32 * RT), ncq = (nt + 3) / 4;
+  const int nrg = (nt + 32 * RT - 1) / (32 * RT), ncq = (nt + 3) >> 2;
   for (int tile = warp; tile < nrg * ncq; tile += nw) {
-    const int rg = tile % nrg, cq = tile / nrg;
+    const int cq = tile / nrg, rg = tile - cq * nrg;
     const int R0 = s + 32 * RT * rg + lane, l0 = s + 4 * cq;
-    double acc[RT][4], old[RT][4];
+    double acc[RT][4];
 #pragma unroll
     for (int a = 0; a < RT; ++a)
 #pragma unroll
-      for (int b = 0; b < 4; ++b) {
-        acc[a][b] = 0.0;
-        const int r = R0 + 32 * a, l = l0 + b;
-        old[a][b] = (r < k && l < k) ? A[r + (size_t)l * ld] : 0.0;
-      }
-    for (int t = 0; t < pb; ++t) {
-      const double *Vt = V + (size_t)t * kv, *Wt = W + (size_t)t * kv;
-      double vr[RT], wr[RT], vl[4], wl[4];
+      for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
+    const bool interior = (s + 32 * RT * (rg + 1) <= k) && (l0 + 4 <= k);  // warp-uniform
+    const double *pv = V, *pw = W;
+    if (interior) {
+      for (int t = 0; t < pb; ++t, pv += kv, pw += kv) {
+        double vr[RT], wr[RT], vl[4], wl[4];
 #pragma unroll
-      for (int a = 0; a < RT; ++a) {
-        const int r = R0 + 32 * a;
-        vr[a] = r < k ? Vt[r] : 0.0;
-        wr[a] = r < k ? Wt[r] : 0.0;
+        for (int a = 0; a < RT; ++a) {
+          vr[a] = pv[R0 + 32 * a];
+          wr[a] = pw[R0 + 32 * a];
+        }
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          vl[b] = pv[l0 + b];
+          wl[b] = pw[l0 + b];
+        }
+#pragma unroll
+        for (int a = 0; a < RT; ++a)
+#pragma unroll
+          for (int b = 0; b < 4; ++b) acc[a][b] = fma(vr[a], wl[b], fma(wr[a], vl[b], acc[a][b]));
       }
 #pragma unroll
       for (int b = 0; b < 4; ++b) {
-        vl[b] = l0 + b < k ? Vt[l0 + b] : 0.0;
-        wl[b] = l0 + b < k ? Wt[l0 + b] : 0.0;
+        AP col = A + (size_t)(l0 + b) * ld + R0;
+#pragma unroll
+        for (int a = 0; a < RT; ++a) col[32 * a] -= acc[a][b];
+      }
+    } else {
+      for (int t = 0; t < pb; ++t, pv += kv, pw += kv) {
+        double vr[RT], wr[RT], vl[4], wl[4];
+#pragma unroll
+        for (int a = 0; a < RT; ++a) {
+          const int r = R0 + 32 * a;
+          vr[a] = r < k ? pv[r] : 0.0;
+          wr[a] = r < k ? pw[r] : 0.0;
+        }
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          vl[b] = l0 + b < k ? pv[l0 + b] : 0.0;
+          wl[b] = l0 + b < k ? pw[l0 + b] : 0.0;
+        }
+#pragma unroll
+        for (int a = 0; a < RT; ++a)
+#pragma unroll
+          for (int b = 0; b < 4; ++b) acc[a][b] = fma(vr[a], wl[b], fma(wr[a], vl[b], acc[a][b]));
       }
 #pragma unroll
       for (int a = 0; a < RT; ++a)
 #pragma unroll
-        for (int b = 0; b < 4; ++b) acc[a][b] = fma(vr[a], wl[b], fma(wr[a], vl[b], acc[a][b]));
+        for (int b = 0; b < 4; ++b) {
+          const int r = R0 + 32 * a, l = l0 + b;
+          if (r < k && l < k) A[r + (size_t)l * ld] -= acc[a][b];
+        }
+    }
+  }
+}
+
+// One share of p = A v (rows c+1 .. k-1): a warp takes R row blocks (rows row0 + 32 a) and a contiguous
+// range of columns; the column pointer steps by ld, the row offsets are immediates.  Rows >= k read
+// whatever follows (the caller pads the allocation) and are masked when the partial sums are stored.
+// part[((item * R) + a) * 32 + lane].
+template <int R, typename AP>
+__device__ __forceinline__ void symv_part(AP A, int ld, int k, int c, const double *vi, double *part, int warp,
+                                          int lane, int nw) {
+  const int m = k - c - 1;
+  const int ngrp = (m + 32 * R - 1) / (32 * R);
+  int lg = 0;  // nsplit = largest power of two <= nw / ngrp
+  while ((ngrp << (lg + 1)) <= nw) ++lg;
+  const int nsplit = 1 << lg;
+  for (int item = warp; item < (ngrp << lg); item += nw) {
+    const int g = item >> lg, sp = item & (nsplit - 1);
+    const int row0 = c + 1 + 32 * R * g + lane;
+    const int lb = c + 1 + ((m * sp) >> lg), le = c + 1 + ((m * (sp + 1)) >> lg);
+    double acc[R];
+#pragma unroll
+    for (int a = 0; a < R; ++a) acc[a] = 0.0;
+    AP pa = A + (size_t)lb * ld + row0;
+    int l = lb;
+    for (; l + 4 <= le; l += 4) {
+      double x[4][R];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+#pragma unroll
+        for (int a = 0; a < R; ++a) x[u][a] = pa[32 * a];
+        pa += ld;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const double vl = vi[l + u];
+#pragma unroll
+        for (int a = 0; a < R; ++a) acc[a] = fma(x[u][a], vl, acc[a]);
+      }
+    }
+    for (; l < le; ++l, pa += ld) {
+      const double vl = vi[l];
+#pragma unroll
+      for (int a = 0; a < R; ++a) acc[a] = fma(pa[32 * a], vl, acc[a]);
     }
 #pragma unroll
-    for (int a = 0; a < RT; ++a)
-#pragma unroll
-      for (int b = 0; b < 4; ++b) {
-        const int r = R0 + 32 * a, l = l0 + b;
-        if (r < k && l < k) A[r + (size_t)l * ld] = old[a][b] - acc[a][b];
-      }
+    for (int a = 0; a < R; ++a) part[(item * R + a) * 32 + lane] = (row0 + 32 * a < k) ? acc[a] : 0.0;
   }
 }
 
@@ -103,14 +172,29 @@ __device__ __forceinline__ void apply_reflectors(double (&y)[RPL], const double 
 
 enum { VK_NONE = 0, VK_B = 1, VK_FIELD = 2, VK_WBAR = 3, VK_UNIT = 4 };
 
-template <int RPL>
-__global__ void __launch_bounds__(512)
-    fcn_blk_kernel(FcnArgs a, int a_smem) {
+// shared-memory layout (doubles), shared by the kernel and the host-side size computation
+struct FcnSmem {
+  int kp, nw, part_len, a_len, vw_len, wscr_len, total;
+  __host__ __device__ FcnSmem(int k, int nw_, bool a_smem) {
+    kp = (k + 3) & ~3;
+    nw = nw_;
+    part_len = nw * 4 * 32;
+    a_len = a_smem ? k * k : 0;
+    vw_len = (2 * FCN_NB * kp > 32 * k) ? 2 * FCN_NB * kp : 32 * k;
+    wscr_len = 3 * kp + (k / FCN_SEG + 1) * 32;  // zb[kp], xp[kp], f32 pair [kp], ck
+    total = 5 * kp + 4 * 32 + part_len + a_len + vw_len + FCN_NVW * wscr_len;
+  }
+};
+
+template <int RPL, bool ASMEM>
+__global__ void __launch_bounds__(256, ASMEM ? 1 : 2)
+    fcn_blk_kernel(FcnArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int k = a.k;
   const int tid = threadIdx.x, nt = blockDim.x;
   const int warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
-  const int kp = (k + 3) & ~3;  // padded vector length (row stride of V, W)
+  const FcnSmem L(k, nw, ASMEM);
+  const int kp = L.kp;  // padded vector length (row stride of V, W)
   const int nb = FCN_NB;
   double *sm = reinterpret_cast<double *>(smem_raw);
   double *d = sm;                 // [kp]
@@ -122,36 +206,30 @@ __global__ void __launch_bounds__(512)
   double *red2 = red + 32;        // [32]
   double *s1 = red2 + 32;         // [32]
   double *s2 = s1 + 32;           // [32]
-  double *part = s2 + 32;         // [nw * 32]
-  double *VW = part + nw * 32;    // [2 * nb * kp], later rp[k * 32]
-  const int vw_len = (2 * nb * kp > 32 * k) ? 2 * nb * kp : 32 * k;
-  double *wscr = VW + vw_len;     // FCN_NVW x per-warp scratch
-  const int ckn = (k / FCN_SEG + 1) * 32;
-  const int wscr_len = 3 * kp + ckn;  // zb[kp], xp[kp], f32 pair [kp], ck[ckn]
-  double *As = wscr + FCN_NVW * wscr_len;  // [k * k] when a_smem
+  double *part = s2 + 32;         // [nw * 4 * 32]
+  double *As = part + L.part_len; // [k * k] when ASMEM (reads may run up to 127 rows past a column: VW follows)
+  double *VW = As + L.a_len;      // [2 * nb * kp], later rp[k * 32]
+  double *wscr = VW + L.vw_len;   // FCN_NVW x per-warp scratch
+  const int wscr_len = L.wscr_len;
   __shared__ int s_q;
   __shared__ double s_aedge;
 
   const int64_t unit = blockIdx.x;
   if (unit >= a.nunits) return;
   double *Cg = a.C + unit * (int64_t)k * k;
-  double *A = a_smem ? As : Cg;
+  double *A = ASMEM ? As : Cg;
   const int ld = k;
   double *V = VW, *W = VW + (size_t)nb * kp;
 
   // ---- load / symmetrise (the Gram kernels deliver the column-major lower triangle) ----
   for (int x = tid; x < 2 * nb * kp; x += nt) VW[x] = 0.0;
-  if (a_smem) {
-    for (int x = tid; x < k * k; x += nt) {
-      const int i = x % k, j = x / k;
-      As[x] = i >= j ? Cg[i + (size_t)j * k] : Cg[j + (size_t)i * k];
+  for (int j = warp; j < k; j += nw)
+    for (int i = lane; i < k; i += 32) {
+      if (ASMEM)
+        As[i + j * k] = i >= j ? Cg[i + (size_t)j * k] : Cg[j + (size_t)i * k];
+      else if (i < j)
+        Cg[i + (size_t)j * k] = Cg[j + (size_t)i * k];
     }
-  } else {
-    for (int x = tid; x < k * k; x += nt) {
-      const int i = x % k, j = x / k;
-      if (i < j) Cg[x] = Cg[j + (size_t)i * k];
-    }
-  }
   __syncthreads();
 
   // ---- 1. tridiagonalisation ----
@@ -160,12 +238,16 @@ __global__ void __launch_bounds__(512)
     const int pb = (k - 2 - c0) < nb ? (k - 2 - c0) : nb;
     for (int i = 0; i < pb; ++i) {
       const int c = c0 + i;
+      const int m = k - c - 1;          // rows / columns of the trailing block
+      const int nrb = (m + 31) >> 5;
+      const int RR = nrb >= 4 ? 4 : (nrb >= 2 ? 2 : 1);  // row blocks per warp in the product (CTA-uniform)
       // phase 1: column c with the pending updates of this panel
       double colv = 0.0;
       if (r >= c && r < k) {
         colv = A[r + (size_t)c * ld];
-        for (int t = 0; t < i; ++t)
-          colv -= V[t * kp + r] * W[t * kp + c] + W[t * kp + r] * V[t * kp + c];
+        const double *pv = V + r, *pw = W + r, *qv = V + c, *qw = W + c;
+        for (int t = 0; t < i; ++t, pv += kp, pw += kp, qv += kp, qw += kp)
+          colv -= pv[0] * qw[0] + pw[0] * qv[0];
         xcol[r] = colv;
       }
       {
@@ -178,10 +260,11 @@ __global__ void __launch_bounds__(512)
       double sigma = 0.0;
       for (int w = 0; w < nw; ++w) sigma += red[w];
       const double x1 = xcol[c + 1];
-      const double nrm = sqrt(sigma);
-      const bool zero = nrm == 0.0;
+      const bool zero = !(sigma > 1e-290) && sigma == sigma;  // NaN falls through and propagates
+      const double rn = rsqrt(zero ? 1.0 : sigma);
+      const double nrm = zero ? 0.0 : sigma * rn;
       const double alpha = zero ? 0.0 : -copysign(nrm, x1);
-      const double tauc = zero ? 0.0 : 1.0 / (nrm * (nrm + fabs(x1)));
+      const double tauc = zero ? 0.0 : rn * __drcp_rn(nrm + fabs(x1));
       const double v_r = (r == c + 1) ? x1 - alpha : ((r > c + 1 && r < k) ? colv : 0.0);
       if (r < k) V[i * kp + r] = v_r;
       if (tid == 0) {
@@ -192,36 +275,13 @@ __global__ void __launch_bounds__(512)
       __syncthreads();
       // phase 3: p = A v over rows c+1.., split over the warps; dots of v with the panel's V, W
       {
-        const int m = k - c - 1;
-        const int nrb = (m + 31) >> 5;
-        const int nsplit = nw / nrb > 1 ? nw / nrb : 1;
         const double *vi = V + i * kp;
-        for (int item = warp; item < nrb * nsplit; item += nw) {
-          const int rb = item / nsplit, sp = item - rb * nsplit;
-          int row = c + 1 + 32 * rb + lane;
-          const bool rowok = row < k;
-          row = rowok ? row : k - 1;
-          const int lb = c + 1 + (int)(((long long)m * sp) / nsplit);
-          const int le = c + 1 + (int)(((long long)m * (sp + 1)) / nsplit);
-          const double *Ar = A + row;
-          double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
-          int l = lb;
-          for (; l + 8 <= le; l += 8) {
-            double x[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) x[u] = Ar[(size_t)(l + u) * ld];
-            acc0 = fma(x[0], vi[l + 0], acc0);
-            acc1 = fma(x[1], vi[l + 1], acc1);
-            acc2 = fma(x[2], vi[l + 2], acc2);
-            acc3 = fma(x[3], vi[l + 3], acc3);
-            acc0 = fma(x[4], vi[l + 4], acc0);
-            acc1 = fma(x[5], vi[l + 5], acc1);
-            acc2 = fma(x[6], vi[l + 6], acc2);
-            acc3 = fma(x[7], vi[l + 7], acc3);
-          }
-          for (; l < le; ++l) acc0 = fma(Ar[(size_t)l * ld], vi[l], acc0);
-          part[item * 32 + lane] = rowok ? (acc0 + acc1) + (acc2 + acc3) : 0.0;
-        }
+        if (RR == 4)
+          symv_part<4>(A, ld, k, c, vi, part, warp, lane, nw);
+        else if (RR == 2)
+          symv_part<2>(A, ld, k, c, vi, part, warp, lane, nw);
+        else
+          symv_part<1>(A, ld, k, c, vi, part, warp, lane, nw);
         for (int dt = warp; dt < 2 * i; dt += nw) {
           const int t = dt >> 1;
           const double *src = (dt & 1) ? V + t * kp : W + t * kp;
@@ -235,17 +295,21 @@ __global__ void __launch_bounds__(512)
       // phase 4: p = tau (A_eff v), K = tau/2 p.v
       double pr = 0.0;
       if (r > c && r < k) {
-        const int m = k - c - 1;
-        const int nrb = (m + 31) >> 5;
-        const int nsplit = nw / nrb > 1 ? nw / nrb : 1;
+        const int lgR = RR == 4 ? 2 : (RR == 2 ? 1 : 0);
+        const int ngrp = (nrb + RR - 1) >> lgR;
+        int lg = 0;
+        while ((ngrp << (lg + 1)) <= nw) ++lg;
         const int rr = r - (c + 1), rb = rr >> 5, ln = rr & 31;
-        for (int sp = 0; sp < nsplit; ++sp) pr += part[(rb * nsplit + sp) * 32 + ln];
-        for (int t = 0; t < i; ++t) pr -= V[t * kp + r] * s1[t] + W[t * kp + r] * s2[t];
+        const int g = rb >> lgR, ai = rb & (RR - 1);
+        const double *pp = part + (((g << lg) * RR + ai) << 5) + ln;
+        for (int sp = 0; sp < (1 << lg); ++sp, pp += RR * 32) pr += pp[0];
+        const double *pv = V + r, *pw = W + r;
+        for (int t = 0; t < i; ++t, pv += kp, pw += kp) pr -= pv[0] * s1[t] + pw[0] * s2[t];
         pr *= tauc;
       }
       {
-        double pv = wsum(pr * v_r);
-        if (lane == 0) red2[warp] = pv;
+        double pvs = wsum(pr * v_r);
+        if (lane == 0) red2[warp] = pvs;
       }
       __syncthreads();
       // phase 5: w = p - K v; store the reflector over the eliminated column
@@ -445,37 +509,47 @@ __global__ void __launch_bounds__(512)
 }  // namespace
 
 size_t fcn_blk_smem(int k, int threads, bool a_smem) {
-  const int kp = (k + 3) & ~3, nw = threads / 32;
-  const size_t vw = std::max<size_t>((size_t)2 * FCN_NB * kp, (size_t)32 * k);
-  const size_t wscr = (size_t)3 * kp + (size_t)(k / FCN_SEG + 1) * 32;
-  size_t n = (size_t)5 * kp + 4 * 32 + (size_t)nw * 32 + vw + FCN_NVW * wscr;
-  if (a_smem) n += (size_t)k * k;
-  return n * sizeof(double);
+  return sizeof(double) * (size_t)FcnSmem(k, threads / 32, a_smem).total;
 }
 
 void launch_fcn_solve(cudaStream_t s, const FcnArgs &a) {
   if (a.nunits == 0) return;
   const int k = a.k;
   LK_REQUIRE(k >= 2 && k <= LETKF_B200_MAX_MEMBERS, "fcn solver: need 2 <= k <= 256");
-  int threads = ((2 * k + 31) / 32) * 32;
-  threads = std::max(64, std::min(512, threads));
-  const bool a_smem = fcn_blk_smem(k, threads, true) <= 220 * 1024;
+  // one thread per matrix row in the panel phases
+  const int threads = std::max(64, ((k + 31) / 32) * 32);
+  // the matrix stays in shared memory only while two CTAs still fit on an SM (other units' barriers and
+  // reflector chains then overlap); larger matrices are processed in place in global memory (L2)
+  const bool a_smem = fcn_blk_smem(k, threads, true) <= 110 * 1024;
   const size_t smem = fcn_blk_smem(k, threads, a_smem);
   LK_REQUIRE(a.nunits < ((int64_t)1 << 31), "fcn solver: too many units for one launch");
   auto launch = [&](auto kern) {
     LK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<(unsigned)a.nunits, threads, smem, s>>>(a, a_smem ? 1 : 0);
+    kern<<<(unsigned)a.nunits, threads, smem, s>>>(a);
   };
+#define LK_FCN_CASE(R)                                   \
+  case R:                                                \
+    if (a_smem)                                          \
+      launch(fcn_blk_kernel<R, true>);                   \
+    else                                                 \
+      launch(fcn_blk_kernel<R, false>);                  \
+    break;
   switch ((k + 31) / 32) {
-    case 1: launch(fcn_blk_kernel<1>); break;
-    case 2: launch(fcn_blk_kernel<2>); break;
-    case 3: launch(fcn_blk_kernel<3>); break;
-    case 4: launch(fcn_blk_kernel<4>); break;
-    case 5: launch(fcn_blk_kernel<5>); break;
-    case 6: launch(fcn_blk_kernel<6>); break;
-    case 7: launch(fcn_blk_kernel<7>); break;
-    default: launch(fcn_blk_kernel<8>); break;
+    LK_FCN_CASE(1)
+    LK_FCN_CASE(2)
+    LK_FCN_CASE(3)
+    LK_FCN_CASE(4)
+    LK_FCN_CASE(5)
+    LK_FCN_CASE(6)
+    LK_FCN_CASE(7)
+    default:
+      if (a_smem)
+        launch(fcn_blk_kernel<8, true>);
+      else
+        launch(fcn_blk_kernel<8, false>);
+      break;
   }
+#undef LK_FCN_CASE
   LK_CUDA(cudaGetLastError());
 }
 

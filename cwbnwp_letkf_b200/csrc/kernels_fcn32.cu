@@ -37,11 +37,18 @@ __device__ __forceinline__ void apply_q32(const double (&a)[K32], const double *
   }
 }
 
-// sequential (member 0..31) real32 sum of one value per lane, as the oracle defines sum()
-__device__ __forceinline__ float seq_sum32f(float v) {
+// sequential (member 0..31) real32 sum of one value per lane, as the oracle defines sum(): the values go
+// through 128 bytes of shared memory (8 broadcast loads) instead of 32 dependent shuffles
+__device__ __forceinline__ float seq_sum32f(float v, float *buf, int lane) {
+  __syncwarp();
+  buf[lane] = v;
+  __syncwarp();
   float s = 0.f;
 #pragma unroll
-  for (int m = 0; m < 32; ++m) s = LK_ADD(s, __shfl_sync(FULLF, v, m));
+  for (int m = 0; m < 32; m += 4) {
+    const float4 t = *reinterpret_cast<const float4 *>(buf + m);
+    s = LK_ADD(LK_ADD(LK_ADD(LK_ADD(s, t.x), t.y), t.z), t.w);
+  }
   return s;
 }
 
@@ -53,8 +60,10 @@ constexpr int SM_T = 128;                 // 32 tau
 constexpr int SM_GB = 160;                // 32 g_b
 constexpr int SM_Z = 192;                 // 32 work vector
 constexpr int SM_CK = 224;                // 96 check points
-constexpr int SM_RP = 320;                // 1024 reciprocal pivots
-constexpr int SM_WARP = 320 + 1024;       // 1344 doubles = 10.5 KB
+constexpr int SM_F = 320;                 // 16 doubles = 32 floats: sequential-sum staging
+constexpr int SM_X = 336;                 // 32 xb'
+constexpr int SM_RP = 368;                // 1024 reciprocal pivots
+constexpr int SM_WARP = 368 + 1024;       // 1392 doubles = 10.9 KB
 
 template <int MINB>
 __global__ void __launch_bounds__(128, MINB) fcn32_kernel(FcnArgs A) {
@@ -64,7 +73,8 @@ __global__ void __launch_bounds__(128, MINB) fcn32_kernel(FcnArgs A) {
   if (unit >= A.nunits) return;
   double *sm = reinterpret_cast<double *>(smem_raw) + (size_t)w * SM_WARP;
   double *vw = sm + SM_VW, *dd = sm + SM_D, *ee = sm + SM_E, *tt = sm + SM_T, *gb = sm + SM_GB, *zz = sm + SM_Z;
-  double *ck = sm + SM_CK, *rp = sm + SM_RP;
+  double *ck = sm + SM_CK, *rp = sm + SM_RP, *xs = sm + SM_X;
+  float *fb = reinterpret_cast<float *>(sm + SM_F);
 
   double a[K32];
   {
@@ -141,62 +151,76 @@ __global__ void __launch_bounds__(128, MINB) fcn32_kernel(FcnArgs A) {
   const double sk = sqrt(31.0);
   const float ninv = LK_DIV(1.0f, 32.0f);
 
-  // ---- b: g_b = T^(-1/2) Q^T b ----
-  {
-    double y[1] = {A.bvec[unit * K32 + lane]};
-    apply_q32<1, true>(a, tt, y, lane);
-    gb[lane] = y[0];
-    __syncwarp();
-    pole_solve(gb, K32, ee, rp, cw, ck, lane);
-  }
-  const double gbl = gb[lane];
-
-  // ---- fields (all levels that share these weights) ----
-  if (A.var)
-    for (int lev = 0; lev < A.nz; ++lev)
-      for (int f = 0; f < A.nfields; ++f) {
-        const int64_t pt = A.pt_base + (int64_t)lev * A.level_stride + upt;
-        float *v = A.var + (int64_t)f * A.npts_total * K32;
-        const float xb = v[(int64_t)lane * A.npts_total + pt];          // core:228
-        const double xmean = (double)LK_MUL(seq_sum32f(xb), ninv);      // core:671 (real32)
-        const double xp = (double)xb - xmean;                           // core:672
-        double y[1] = {xp};
-        apply_q32<1, true>(a, tt, y, lane);
-        zz[lane] = y[0];
-        __syncwarp();
-        pole_solve(zz, K32, ee, rp, cw, ck, lane);
-        y[0] = zz[lane];
-        const double sdot = wsum(y[0] * gbl);                           // xb' . wbar (core:673)
-        apply_q32<1, false>(a, tt, y, lane);
-        double xa = xmean + (sdot + sk * y[0]);                         // core:673-675
-        if (isnan_unit) xa = xa * (double)NAN;
-        if (A.xa_raw) A.xa_raw[pt * K32 + lane] = xa;
-        float xa32 = (float)xa;                                         // core:679
-        if (A.use_rtpp || A.use_rtps) {                                 // core:684-698
-          const float xa_mean = LK_MUL(seq_sum32f(xa32), ninv);
-          float xap = LK_SUB(xa32, xa_mean);
-          if (A.use_rtpp) {
-            const float t1 = LK_MUL(LK_SUB(1.0f, A.rtpp_alpha), xap);
-            xap = (float)((double)t1 + (double)A.rtpp_alpha * xp);
-          }
-          if (A.use_rtps) {
-            double dsum = 0;
-#pragma unroll
-            for (int m = 0; m < 32; ++m) {
-              const double x = __shfl_sync(FULLF, xp, m);
-              dsum += x * x;
-            }
-            const float xb_std = (float)dsum;
-            const float xa_std = seq_sum32f(LK_MUL(xap, xap));
-            const float fac =
-                LK_ADD(LK_SUB(LK_MUL(A.rtps_alpha, LK_SQRT(LK_DIV(xb_std, xa_std))), A.rtps_alpha), 1.0f);
-            xap = LK_MUL(xap, fac);
-          }
-          xa32 = LK_ADD(xa_mean, xap);                                  // core:697
-        }
-        v[(int64_t)lane * A.npts_total + pt] = xa32;                    // core:229
-        __syncwarp();
+  // ---- b and the first field together (two independent reflector chains overlap) ----
+  const bool have_field = A.var != nullptr && A.nz > 0 && A.nfields > 0;
+  double gbl;
+  bool first = true;
+  for (int lev = 0; lev < (have_field ? A.nz : 1); ++lev)
+    for (int f = 0; f < (have_field ? A.nfields : 1); ++f) {
+      const int64_t pt = A.pt_base + (int64_t)lev * A.level_stride + upt;
+      float *v = have_field ? A.var + (int64_t)f * A.npts_total * K32 : nullptr;
+      float xb = 0.f;
+      double xmean = 0.0, xp = 0.0;
+      if (have_field) {
+        xb = v[(int64_t)lane * A.npts_total + pt];                         // core:228
+        xmean = (double)LK_MUL(seq_sum32f(xb, fb, lane), ninv);            // core:671 (real32)
+        xp = (double)xb - xmean;                                           // core:672
       }
+      double y;
+      if (first) {
+        double yy[2] = {A.bvec[unit * K32 + lane], xp};
+        apply_q32<2, true>(a, tt, yy, lane);
+        gb[lane] = yy[0];
+        __syncwarp();
+        pole_solve(gb, K32, ee, rp, cw, ck, lane);  // g_b = T^(-1/2) Q^T b
+        gbl = gb[lane];
+        y = yy[1];
+        first = false;
+      } else {
+        double yy[1] = {xp};
+        apply_q32<1, true>(a, tt, yy, lane);
+        y = yy[0];
+      }
+      if (!have_field) break;
+      zz[lane] = y;
+      __syncwarp();
+      pole_solve(zz, K32, ee, rp, cw, ck, lane);
+      double yy[1] = {zz[lane]};
+      const double sdot = wsum(yy[0] * gbl);                               // xb' . wbar (core:673)
+      apply_q32<1, false>(a, tt, yy, lane);
+      double xa = xmean + (sdot + sk * yy[0]);                             // core:673-675
+      if (isnan_unit) xa = xa * (double)NAN;
+      if (A.xa_raw) A.xa_raw[pt * K32 + lane] = xa;
+      float xa32 = (float)xa;                                              // core:679
+      if (A.use_rtpp || A.use_rtps) {                                      // core:684-698
+        const float xa_mean = LK_MUL(seq_sum32f(xa32, fb, lane), ninv);
+        float xap = LK_SUB(xa32, xa_mean);
+        if (A.use_rtpp) {
+          const float t1 = LK_MUL(LK_SUB(1.0f, A.rtpp_alpha), xap);
+          xap = (float)((double)t1 + (double)A.rtpp_alpha * xp);
+        }
+        if (A.use_rtps) {
+          __syncwarp();
+          xs[lane] = xp;
+          __syncwarp();
+          double dsum = 0;  // dot_product(xb', xb') in working precision, sequential like the oracle
+#pragma unroll
+          for (int m = 0; m < 32; m += 2) {
+            const double2 t = *reinterpret_cast<const double2 *>(xs + m);
+            dsum += t.x * t.x;
+            dsum += t.y * t.y;
+          }
+          const float xb_std = (float)dsum;
+          const float xa_std = seq_sum32f(LK_MUL(xap, xap), fb, lane);
+          const float fac =
+              LK_ADD(LK_SUB(LK_MUL(A.rtps_alpha, LK_SQRT(LK_DIV(xb_std, xa_std))), A.rtps_alpha), 1.0f);
+          xap = LK_MUL(xap, fac);
+        }
+        xa32 = LK_ADD(xa_mean, xap);                                       // core:697
+      }
+      v[(int64_t)lane * A.npts_total + pt] = xa32;                         // core:229
+      __syncwarp();
+    }
 
   // ---- parity dump: wbar = Q T^(-1/2) g_b, Wa = sqrt(k-1) Q T^(-1/2) Q^T ----
   if (A.wbar_out) {
