@@ -9,10 +9,16 @@ observations, variable `T` (GTS + radial velocity, the heaviest localisation mix
                  timed with CUDA events on the library's stream, max over ranks.
   e2e          : same metric through the host-pointer C-ABI call (letkf_b200_analyze) with pinned
                  HOST buffers; H2D of xyz+ensemble and D2H of the analysis inside the timed region.
-  roofline     : dominant kernel (the batched eigensolver) against the FP64 FMA peak measured by
-                 the committed micro-benchmark (letkf_b200_fma_peak); per-stage numbers in `stages`.
+  roofline     : dominant kernel against the FP64 FMA peak measured by the committed micro-benchmark
+                 (letkf_b200_fma_peak) or the HBM copy bandwidth of MEASURED_PEAKS.json; per-stage
+                 numbers in `stages`.
   cpu_baseline : the oracle (a port of the reference algorithm; the Fortran reference cannot be
                  compiled here) on the host cores over a bounded sample of the same workload.
+  parity       : the GPU path through the C ABI against the oracle on the SAME sampled points and field
+                 the cpu_baseline leg just analysed (lists, yo/Yb rows, weights, field, NaN sites); a
+                 violated bar makes the run exit with status 3 after printing the line.
+  secondary    : the other two thirds of BASELINE.json's metric, time bounded: config L (256 members)
+                 on a 96x96x50 sub-grid, and config E (batched eigensolves/s, distinct matrices).
 
 `--impl reference` times that CPU restatement alone.  N > 1 (torchrun): grid columns are
 partitioned cyclically across ranks as in module_mpi_util.f90:73-188, observations replicated with
@@ -34,6 +40,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 VAR = os.environ.get("LETKF_BENCH_VAR", "T")
+EXIT_CODE = 0
 
 
 def parse():
@@ -50,6 +57,9 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--no-secondary", action="store_true", help="skip the config L / config E block")
+    ap.add_argument("--parity-points", type=int, default=256,
+                    help="points of the cpu_baseline sample on which lists / rows / weights are compared")
     ap.add_argument("--nxb", type=int, default=0,
                     help="block size along x of the block-cyclic column decomposition (the reference's nxb, "
                          "module_mpi_util.f90:10; results do not depend on it); 0 = the largest of 16, 8, .. 1 "
@@ -105,7 +115,7 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def cpu_baseline(sc, cfg, seconds: float, threads: int):
+def cpu_baseline(sc, cfg, seconds: float, threads: int, keep=None):
     """Oracle (port of the reference hot path) on the host cores over a bounded random sample of the
     workload's grid points, full observation set.  Returns points/s and what the sample was."""
     from oracle import oracle as O
@@ -115,10 +125,7 @@ def cpu_baseline(sc, cfg, seconds: float, threads: int):
     rng = np.random.default_rng(11)
     from cwbnwp_letkf_b200 import synthetic as S
 
-    def run(n):
-        sel = np.sort(rng.choice(sc.npts, n, replace=False))
-        xyz = np.ascontiguousarray(sc.xyz_grid[sel])
-        f = S.make_field(rng, sc.k, xyz, 280.0, 5.0, 1.0)
+    def run_on(n, xyz, f0, f):
         orc.build_tree(cfg)                       # build time excluded, like the GPU tree cache
         t0 = time.perf_counter()
         from oracle.oracle import lib, to_c, _p
@@ -128,17 +135,171 @@ def cpu_baseline(sc, cfg, seconds: float, threads: int):
                               _p(f), threads, ctypes.byref(npo), ctypes.byref(rows))
         dt = time.perf_counter() - t0
         assert rc == 0
-        return dt, npo.value, rows.value
+        return dt, npo.value, rows.value, (xyz, f0, f)
+
+    def run(n):
+        sel = np.sort(rng.choice(sc.npts, n, replace=False))
+        xyz = np.ascontiguousarray(sc.xyz_grid[sel])
+        f0 = S.make_field(rng, sc.k, xyz, 280.0, 5.0, 1.0)
+        return run_on(n, xyz, f0, f0.copy())
 
     pilot = min(2000, sc.npts)
-    dt, _, _ = run(pilot)
+    dt, _, _, _ = run(pilot)
     n = int(min(sc.npts, max(pilot, pilot * seconds / max(dt, 1e-3))))
-    dt, npo, rows = run(n)
+    dt, npo, rows, sample = run(n)
+    if keep is not None:
+        keep["orc"], keep["sample"], keep["npo"], keep["rows"] = orc, sample, npo, rows
     return {"value": n / dt, "unit": "grid points/s", "cores": threads, "kind": "port",
             "sample": f"{n} random grid points of the {sc.nx}x{sc.ny}x{sc.nz} grid, full obs set, variable {cfg_name(cfg)}, "
                       f"{npo} analysed, {rows / max(npo, 1):.0f} rows/point, {dt:.1f} s; oracle = C++ port of the "
                       "reference loop with OpenBLAS dsyrk/dsyevd/dgemm, one OpenMP thread per core",
             "seconds": dt}
+
+
+def load_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return {}
+
+
+def stage_report(stats, k: int, fma64: float, members: int):
+    """Per-stage achieved rates against their rooflines (SURVEY.md 8(d) algorithmic counts) and the roofline
+    object of the dominant stage.  `solve` is the kernel that replaces module_eigen + the weight application:
+    its contract figure uses the 4k^3 LAPACK model of SURVEY 8(d); the flops it really executes
+    (4/3 k^3 tridiagonalisation + O(k^2) per vector) are reported beside it."""
+    peaks = load_peaks()
+    hbm = peaks.get("hbm_gbs", 6650.0)
+    units, rows0 = stats.units, stats.rows
+    ntree_bytes = 12 * stats.npts + 8 * rows0   # xyz in + (idx, r2) written for kept entries
+    ms_solve = stats.ms_eigen + stats.ms_transform
+    executed = (4.0 / 3.0) * k**3 + 2 * 8.0 * k * k + 3 * 32 * 8.0 * k   # tridiagonalisation + Q applications + poles
+    stage = {
+        "search": {"ms": stats.ms_search, "bound": "hbm", "achieved": ntree_bytes / max(stats.ms_search, 1e-9) / 1e6,
+                   "peak": hbm, "unit": "GB/s"},
+        "gram": {"ms": stats.ms_gram, "bound": "fp64",
+                 "achieved": (k * (k + 1) + 2 * k) * rows0 / max(stats.ms_gram, 1e-9) / 1e9, "peak": fma64,
+                 "unit": "TFLOP/s", "gathered_GBs": (4 * k + 8) * rows0 / max(stats.ms_gram, 1e-9) / 1e6},
+        "solve": {"ms": ms_solve, "bound": "fp64", "achieved": 4.0 * k**3 * units / max(ms_solve, 1e-9) / 1e9,
+                  "peak": fma64, "unit": "TFLOP/s", "solves_per_s": units / max(ms_solve, 1e-9) * 1e3,
+                  "model": "4k^3 flop per unit (SURVEY 8(d): ?syevd + 2 ?gemm, the reference's count)",
+                  "executed_TFLOPs": executed * units / max(ms_solve, 1e-9) / 1e9,
+                  "executed_model": "4/3 k^3 (Householder tridiagonalisation) + 16 k^2 (Q^T, Q on two vectors) + "
+                                    "768 k (32 shifted tridiagonal solves) per unit: no eigendecomposition",
+                  "includes": "weight application + RTPP/RTPS epilogue (xb in, xa out: 8k bytes per unit and field)"},
+        "tree_build_ms": stats.ms_tree,
+    }
+    for s_ in ("search", "gram", "solve"):
+        stage[s_]["frac"] = stage[s_]["achieved"] / stage[s_]["peak"] if stage[s_]["ms"] > 0 else None
+        stage[s_]["share_of_step"] = stage[s_]["ms"] / max(stats.ms_total, 1e-9)
+    # DRAM traffic per launch: NOT measured in this run -- taken from the committed ncu --set full capture
+    try:
+        tt = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+    except Exception:
+        tt = {}
+    tab = tt.get("k%d" % members, {})
+    per_launch_units = min(units, 1 << 18)
+    for s_ in ("search", "gram", "solve"):
+        t_ = tab.get(s_)
+        stage[s_]["traffic_bytes_per_launch"] = t_["bytes_per_unit"] * per_launch_units if t_ else None
+        stage[s_]["algorithmic_bytes_per_unit"] = t_.get("algorithmic_bytes_per_unit") if t_ else None
+    dom = max(("search", "gram", "solve"), key=lambda s_: stage[s_]["ms"])
+    roofline = {"kernel": dom, "bound": stage[dom]["bound"], "achieved": stage[dom]["achieved"],
+                "peak": stage[dom]["peak"], "unit": stage[dom]["unit"], "frac": stage[dom]["frac"],
+                "traffic": stage[dom]["traffic_bytes_per_launch"],
+                "traffic_source": ("committed ncu --set full capture %s (tree %s), scaled by the units of one launch; "
+                                   "not measured in this run" % (tt.get("source", "profiles/ncu_traffic.json"),
+                                                                 tt.get("git", "?"))) if tab else None,
+                "peak_source": ("letkf_b200_fma_peak micro-benchmark (FP64 FMA, measured in this run; "
+                                "MEASURED_PEAKS.json has no FP64 figure)" if stage[dom]["bound"] == "fp64" else
+                                ("MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)")),
+                "share_of_step": stage[dom]["share_of_step"]}
+    return stage, roofline
+
+
+def parity_block(eng, cfg, keep, npoints: int):
+    """GPU (through the C ABI) against the oracle on the sample the cpu_baseline leg analysed."""
+    from oracle import parity as PAR
+    orc = keep["orc"]
+    xyz, f0, fref = keep["sample"]
+    got = f0.copy()
+    st = eng.analyze(cfg, xyz, got)
+    par = PAR.compare_fields(got, fref, f0)
+    par.update(points=int(xyz.shape[0]), analysed=int(st.npts_analysed),
+               counts_equal=bool(st.npts_analysed == keep["npo"] and st.rows == keep["rows"]))
+    n = min(npoints, xyz.shape[0])
+    sel = np.sort(np.random.default_rng(5).choice(xyz.shape[0], n, replace=False))
+    pp = PAR.point_parity(eng, orc, cfg, np.ascontiguousarray(xyz[sel]), np.ascontiguousarray(f0[:, sel]),
+                          strict=False)
+    par.update(weight_points=pp["analysed"], lists_bit_equal=pp["lists_bit_equal"], yoyb_bit_equal=pp["yoyb_bit_equal"],
+               wbar_Wa_max_rel=max(pp["max_rel_wbar"], pp["max_rel_Wa"]), xa_raw_max_rel=pp["max_rel_raw"],
+               rows_per_point=pp["rows"] / max(pp["analysed"], 1))
+    par["ok"] = bool(par["counts_equal"] and par["nan_sites_equal"] and par["untouched_bit_identical"] and
+                     par["lists_bit_equal"] and par["yoyb_bit_equal"] and par["wbar_Wa_max_rel"] < 1e-10 and
+                     par["xa_raw_max_rel"] < 1e-10 and par["field_max_rel"] <= 5e-7)
+    par["bars"] = "lists / rows bit-exact, wbar Wa xa_raw < 1e-10, field < 5e-7, NaN sites equal"
+    return par
+
+
+def secondary_L(device: int, budget_s: float = 60.0):
+    """Config L (256 members) on the 96x96x50 sub-grid of config M, variable T: one timed step."""
+    import torch
+    from cwbnwp_letkf_b200 import config as C
+    from cwbnwp_letkf_b200 import host as H
+    from cwbnwp_letkf_b200 import synthetic as S
+    t0 = time.perf_counter()
+    k = 256
+    sc, rng = S.scenario_M(k=k, nx=96, ny=96, nz=50)
+    eng = H.LetkfB200(k, True, device)
+    for o in sc.obs.values():
+        eng.set_obs(o)
+    cfg = C.sample_namelist("T")
+    cfg.tune_q = False
+    dev = torch.device("cuda", device)
+    f0 = S.make_field(np.random.default_rng(77), k, sc.xyz_grid, 280.0, 5.0, 1.0)
+    d_xyz, d_f0 = torch.from_numpy(sc.xyz_grid).to(dev), torch.from_numpy(f0).to(dev)
+    d_var = torch.empty_like(d_f0)
+    ccfg = C.to_c(cfg)
+    stream = torch.cuda.ExternalStream(eng.stream_ptr, device=dev)
+    fma64 = eng.fma_peak(0)
+    t_setup = time.perf_counter() - t0
+    ms, st, steps = [], None, 0
+    for it in range(3):                       # 1 warm-up + up to 2 timed steps inside the budget
+        d_var.copy_(d_f0)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        st = eng.analyze_ptr(ccfg, sc.npts, d_xyz.data_ptr(), 1, d_var.data_ptr(), dev=True)
+        e1.record(stream)
+        e1.synchronize()
+        if it > 0:
+            ms.append(e0.elapsed_time(e1))
+        if it > 0 and time.perf_counter() - t0 > budget_s:
+            break
+    stage, roofline = stage_report(st, k, fma64, k)
+    out = {"workload": "L: 96x96x50 sub-grid of config M (same generator: %d obs values), k=256, variable T" %
+                       sc.total_obs_values(),
+           "metric": "analysed grid points/s", "value": sc.npts / (np.mean(ms) * 1e-3), "unit": "grid points/s",
+           "ms_per_step": float(np.mean(ms)), "steps": len(ms), "warmup": 1, "dtype": "f64",
+           "rows_per_analysed_point": st.rows / max(st.npts_analysed, 1), "roofline": roofline, "stages": stage,
+           "setup_s": t_setup}
+    eng.finalize()
+    del d_xyz, d_f0, d_var
+    torch.cuda.empty_cache()
+    return out
+
+
+def secondary_E(device: int, budget_s: float = 40.0):
+    """Config E: batched eigensolves/s (values + vectors) over DISTINCT matrices, FP64 and FP32."""
+    import bench_eig
+    out = []
+    cases = [(k, dt) for dt in ("f64", "f32") for k in (32, 64, 128, 256)]
+    per = budget_s / len(cases)
+    for k, dt in cases:
+        r = bench_eig.run_case(k, dt, total=1_000_000, budget_s=0.6 * per, sample=64, cpu=False, device=device)
+        out.append({q: r[q] for q in ("k", "dtype", "value", "unit", "matrices_solved", "distinct", "max_sweeps",
+                                      "frac_of_fma_peak_4k3_model", "fma_peak_tflops", "check")})
+    return out
 
 
 def cfg_name(cfg):
@@ -334,84 +495,38 @@ def main():
         return
 
     # ---- roofline (SURVEY.md 8(d) algorithmic counts) from the last timed step of rank 0 ----
-    units = stats.units
-    rows0 = stats.rows
-    ntree_bytes = 12 * stats.npts + 8 * rows0          # xyz in + (idx,r2) written for kept entries (approx: rows ~ entries)
-    stage = {
-        "search": {"ms": stats.ms_search, "bound": "hbm", "achieved": ntree_bytes / (stats.ms_search * 1e-3) / 1e9,
-                   "peak": None, "unit": "GB/s"},
-        "gram": {"ms": stats.ms_gram, "bound": "fp64",
-                 "achieved": (k * (k + 1) + 2 * k) * rows0 / (stats.ms_gram * 1e-3) / 1e12, "peak": fma64,
-                 "unit": "TFLOP/s", "gathered_GBs": (4 * k + 8) * rows0 / (stats.ms_gram * 1e-3) / 1e9},
-        "eigen": {"ms": stats.ms_eigen, "bound": "fp64", "achieved": 4.0 * k**3 * units / (stats.ms_eigen * 1e-3) / 1e12,
-                  "peak": fma64, "unit": "TFLOP/s", "eigensolves_per_s": units / (stats.ms_eigen * 1e-3),
-                  "max_sweeps": stats.max_sweeps,
-                  "mean_sweeps": (stats.sweeps_sum / units) if units and stats.sweeps_sum else None},
-        "transform": {"ms": stats.ms_transform, "bound": "hbm",
-                      "achieved": 8.0 * k * units / (stats.ms_transform * 1e-3) / 1e9, "peak": None, "unit": "GB/s"},
-        "tree_build_ms": stats.ms_tree,
-    }
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    hbm = peaks.get("hbm_gbs", 6650.0)
-    for s_ in ("search", "transform"):
-        stage[s_]["peak"] = hbm
-    if stats.ms_transform < 0.01 * max(stats.ms_eigen, 1e-9):
-        # k = 32 FP64: the transform runs in the eigensolver's epilogue (no separate kernel)
-        stage["transform"].update({"achieved": None, "note": "fused into the eigen kernel epilogue"})
-    for s_ in ("search", "gram", "eigen", "transform"):
-        ok_ = stage[s_]["ms"] > 0 and stage[s_]["achieved"] is not None
-        stage[s_]["frac"] = stage[s_]["achieved"] / stage[s_]["peak"] if ok_ else None
-    # measured DRAM traffic of each stage's kernel from the committed ncu --set full capture
-    try:
-        traffic_tab = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
-    except Exception:
-        traffic_tab = {}
-    per_launch_units = min(units, 1 << 18)
-    tab_k = traffic_tab if a.members == 32 else traffic_tab.get("k%d" % a.members, {})
-    for s_ in ("search", "gram", "eigen", "transform"):
-        t_ = tab_k.get(s_)
-        # per launch = per-unit DRAM bytes of the captured launch x the units one launch of this run processes
-        stage[s_]["traffic_bytes_per_launch"] = (t_["bytes_per_unit"] * min(per_launch_units, t_["units_per_launch"])
-                                                 if a.members != 32 else t_["bytes_per_unit"] * per_launch_units) if t_ else None
-    dom = max(("search", "gram", "eigen", "transform"), key=lambda s_: stage[s_]["ms"])
-    roofline = {"kernel": dom, "bound": stage[dom]["bound"], "achieved": stage[dom]["achieved"],
-                "peak": stage[dom]["peak"], "unit": stage[dom]["unit"], "frac": stage[dom]["frac"], "traffic": stage[dom]["traffic_bytes_per_launch"],
-                "traffic_note": ("DRAM bytes of one launch (2^18 units) from profiles/ncu_traffic.json; the eigen kernel "
-                                 "(with the fused transform) reads C, b, xb and writes xa: algorithmic 8.7 KB per unit, "
-                                 "measured 8.75 KB") if a.members == 32 else
-                                ("DRAM bytes per launch from profiles/ncu_traffic.json[k%d] if captured; at k = 256 the "
-                                 "matrices live in L2 + shared memory and the warm-start products spill to DRAM "
-                                 "(24.6 MB per unit vs 0.8 MB algorithmic)" % a.members),
-                "model": ("achieved = 4k^3 flop per eigensolve (SURVEY 8(d) LAPACK model) x units / device time; the "
-                          "Jacobi kernel executes ~7x that; ncu: FP64 pipe 42% busy, FP64 tensor pipe 7%, issue 52%")
-                         if a.members == 32 else
-                         ("achieved = 4k^3 flop per eigensolve (SURVEY 8(d) LAPACK model) x units / device time; the "
-                          "block Jacobi kernel executes 4k^3 per sweep (see stages.eigen.mean_sweeps); ncu at k = 256: "
-                          "FP64 pipe 32% busy"),
-                "peak_source": ("letkf_b200_fma_peak micro-benchmark (FP64 FMA, measured in this run)"
-                                if stage[dom]["bound"] == "fp64" else
-                                ("MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s")),
-                "share_of_step": stage[dom]["ms"] / max(stats.ms_total, 1e-9)}
+    fma = {"fp64": fma64, "fp32": fma32, "fp64_dmma": dmma64, "fp64_dmma_plus_fma": mixed64}
+    stage, roofline = stage_report(stats, k, fma64, a.members)
 
-    cpu = None
+    cpu, par = None, None
     if not a.no_cpu_baseline:
-        cpu = cpu_baseline(sc, cfg, a.cpu_seconds, os.cpu_count() or 1)
+        keep = {}
+        cpu = cpu_baseline(sc, cfg, a.cpu_seconds, os.cpu_count() or 1, keep)
+        if world == 1:
+            par = parity_block(eng, cfg, keep, a.parity_points)
+        del keep
+
+    secondary = None
+    if world == 1 and not a.no_secondary and a.members == 32 and (a.nx, a.ny, a.nz) == (450, 450, 50):
+        eng.finalize()
+        del d_xyz, d_field0, d_var
+        torch.cuda.empty_cache()
+        secondary = {"config_L_subgrid": secondary_L(local_rank), "config_E_eigensolves": secondary_E(local_rank)}
 
     out = {"metric": "analysed grid points/s", "value": value, "unit": "grid points/s", "n_gpus": world,
            "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-           "stages": stage, "points_analysed": int(analysed), "analysed_fraction": analysed / total_pts,
+           "parity": par, "stages": stage, "points_analysed": int(analysed), "analysed_fraction": analysed / total_pts,
            "points_per_s_analysed_only": analysed / (ms_per_step * 1e-3), "rows_per_analysed_point": rows / max(analysed, 1),
-           "ms_steps": [round(float(x), 2) for x in t_steps], "fma_peak_tflops": {"fp64": fma64, "fp32": fma32, "fp64_dmma": dmma64, "fp64_dmma_plus_fma": mixed64}, "obs_setup_s": t_obs, "wall_s_timed": wall,
-           "obs_values": sc.total_obs_values()}
+           "ms_steps": [round(float(x), 2) for x in t_steps], "fma_peak_tflops": fma, "obs_setup_s": t_obs,
+           "wall_s_timed": wall, "obs_values": sc.total_obs_values(), "secondary": secondary}
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
+    if par is not None and not par["ok"]:
+        global EXIT_CODE
+        EXIT_CODE = 3
 
 
 if __name__ == "__main__":
@@ -437,3 +552,4 @@ if __name__ == "__main__":
         print(l, file=sys.stderr)
     if lines:
         print(lines[-1], flush=True)
+    sys.exit(EXIT_CODE)

@@ -52,7 +52,7 @@ class Projection:
     truelat1: float
     truelat2: float
     sta_lon: float
-    earthradius: float = 6370000.0
+    earthradius: float = 6.37122e6   # module_param.f90:108 (used by module_projection.f90:34,45)
 
     def __post_init__(self):
         f32 = np.float32

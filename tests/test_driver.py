@@ -28,6 +28,30 @@ def test_projection_round_trip():
     assert 95e3 < float(x1) < 108e3
 
 
+def test_projection_known_answer_with_the_reference_constants():
+    """lonlat_to_xy against a float64 evaluation of module_projection.f90:27-50 with the reference's own
+    earthradius = 6.37122e6 (module_param.f90:108) -- an independent restatement, not the Projection class."""
+    cen_lat, t1, t2, sta_lon = 23.5, 10.0, 40.0, 120.5          # input.nml:15-19 style
+    R = 6.37122e6
+    d2r = np.pi / 180.0
+    lat0, lat1, lat2, lon0 = cen_lat * d2r, t1 * d2r, t2 * d2r, sta_lon * d2r
+    cot = lambda x: 1.0 / np.tan(x)
+    n = np.log(np.cos(lat1) / np.cos(lat2)) / np.log(np.tan(0.5 * (0.5 * np.pi + lat2)) * cot(0.5 * (0.5 * np.pi + lat1)))
+    f = np.cos(lat1) * np.exp(n * np.log(np.tan(0.5 * (0.5 * np.pi + lat1)))) / n
+    rh0 = R * f * np.exp(n * np.log(cot(0.5 * (0.5 * np.pi + lat0))))
+    lon = np.array([118.0, 120.5, 123.25, 121.0])
+    lat = np.array([21.5, 23.5, 25.75, 27.0])
+    rh = R * f * np.exp(n * np.log(cot(0.5 * (0.5 * np.pi + lat * d2r))))
+    dl = n * (lon * d2r - lon0)
+    x_ref, y_ref = rh * np.sin(dl), rh0 - rh * np.cos(dl)
+    proj = D.Projection(cen_lat, t1, t2, sta_lon)
+    assert proj.earthradius == 6.37122e6
+    x, y = proj.lonlat_to_xy(lon, lat)
+    # real32 evaluation of rh ~ 1e7 m: a few metres of rounding; the old 6.37e6 radius was ~2 km off
+    assert np.abs(x - x_ref).max() < 30.0 and np.abs(y - y_ref).max() < 30.0
+    assert abs(x[1]) < 1.0 and abs(y[1]) < 30.0                 # the projection centre maps to the origin
+
+
 def test_index_tables_cover_the_grid_once():
     nx, ny = 11, 7
     for world, nxb, nyb in [(1, 1, 1), (2, 1, 1), (4, 1, 1), (6, 2, 3), (8, 1, 2)]:

@@ -188,9 +188,12 @@ def test_jacobi_and_matrix_function_solvers_agree(k, monkeypatch):
         eng.finalize()
     (p0, w0, W0, r0), (p1, w1, W1, r1) = res
     assert np.array_equal(p0, p1) and (p0 > 0).sum() > 10
-    # the Jacobi path stops once a sweep saw only |cos| <= 1e-7 (kernels_eig.cu), good for the 1e-10 bar on the
-    # tested cases but not much better at k = 256; the default path agrees with LAPACK to ~1e-14
-    assert _relerr(w0, w1) < 1e-8 and _relerr(W0, W1) < 1e-8 and _relerr(r0, r1) < 1e-10
+    # the Jacobi path stops once a sweep saw only |cos| <= 1e-7 (kernels_eig.cu): measured against the default
+    # path (which agrees with LAPACK to ~1e-14, test_config_L_observation_density) it is ~1e-11 at k = 160 and
+    # up to 1e-8 (Wa) / 3e-10 (analysis) at k = 256 on this case -- the fallback, not the default
+    tight = k <= 64
+    assert _relerr(w0, w1) < (1e-10 if tight else 5e-8) and _relerr(W0, W1) < (1e-10 if tight else 5e-8)
+    assert _relerr(r0, r1) < (1e-11 if tight else 2e-9)
 
 
 def test_two_contexts_do_not_share_state(monkeypatch):
