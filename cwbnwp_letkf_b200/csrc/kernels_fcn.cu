@@ -3,9 +3,10 @@
 //   1. blocked Householder tridiagonalisation C = Q T Q^T (LAPACK dsytrd / dlatrd organisation: inside
 //      a panel of NB columns the trailing matrix is only READ -- one symmetric matrix-vector product per
 //      column, corrected with the panel's V, W -- and updated once per panel by the rank-2NB product
-//      A -= V W^T + W V^T).  The matrix lives in shared memory for k <= 128, otherwise in place in global
-//      memory (L2): its bytes are then streamed once per column instead of three times, and never more
-//      than 512 KB per CTA are live (the Jacobi path kept three such matrices per CTA).
+//      A -= V W^T + W V^T on the FP64 tensor pipe).  The matrix lives in shared memory while two CTAs still
+//      fit on an SM (k <= ~88), otherwise in place in global memory (L2): its bytes are then streamed once
+//      per column instead of three times, and never more than 512 KB per CTA are live (the Jacobi path kept
+//      three such matrices per CTA).
 //      The reflectors overwrite the eliminated columns (as LAPACK stores them).
 //   2. spectrum bound (Gershgorin of T), pole table row q, LDL^T pivots of T + a beta_j I for the 32 poles.
 //   3. for every vector (b, the field perturbations of every level that shares the weights, unit
@@ -21,74 +22,63 @@ namespace {
 constexpr int FCN_NB = 16;    // panel width
 constexpr int FCN_NVW = 2;    // vectors in flight (one warp each): b and one field column is the common case
 
-// trailing update A[r][l] -= sum_t V[t][r] W[t][l] + W[t][r] V[t][l] for r, l in [s, k): one warp per
-// (group of 32*RT rows, 4 columns); a thread owns rows R0 + lane + 32 a so that every load is coalesced /
-// conflict free.  V, W: [t][kv] in shared memory (zero beyond k).  Interior tiles take the unguarded path.
-template <int RT, typename AP>
-__device__ __forceinline__ void trailing_update(AP A, int ld, int k, int s, int pb, const double *V,
-                                                const double *W, int kv, int warp, int lane, int nw) {
-  const int nt = k - s;
-  const int nrg = (nt + 32 * RT - 1) / (32 * RT), ncq = (nt + 3) >> 2;
-  for (int tile = warp; tile < nrg * ncq; tile += nw) {
-    const int cq = tile / nrg, rg = tile - cq * nrg;
-    const int R0 = s + 32 * RT * rg + lane, l0 = s + 4 * cq;
-    double acc[RT][4];
+__device__ __forceinline__ void dmma884f(double &d0, double &d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(d0), "+d"(d1)
+               : "d"(a), "d"(b));
+}
+
+// Trailing update on the FP64 tensor pipe: A[r][l] -= sum_t P[t][r] Q[t][l] with P = [V; W], Q = [W; V], one
+// warp per 32 x 32 output tile (16 mma.m8n8k4 per 8 fragment loads).  VW: rows [0, nb) = V, [nb, 2nb) = W,
+// row stride kv = 4 (mod 16) doubles so that the fragment loads are bank-conflict free.  Rows [pb, pb4) of
+// V and W must be zero.  One instruction per 256 multiply-adds instead of one per 32.
+template <typename AP>
+__device__ __forceinline__ void trailing_update_dmma(AP A, int ld, int k, int s, int pb, const double *VW, int kv,
+                                                     int nb, int warp, int lane, int nw) {
+  const int nt = k - s, nt32 = (nt + 31) >> 5;
+  const int lr = lane >> 2, lc = lane & 3;
+  const int pb4 = (pb + 3) & ~3;
+  for (int tile = warp; tile < nt32 * nt32; tile += nw) {
+    const int tj = tile / nt32, ti = tile - tj * nt32;
+    const int r0 = s + 32 * ti, l0 = s + 32 * tj;
+    const bool interior = r0 + 32 <= k && l0 + 32 <= k;  // warp-uniform
+    double acc[4][4][2];
 #pragma unroll
-    for (int a = 0; a < RT; ++a)
+    for (int I = 0; I < 4; ++I)
 #pragma unroll
-      for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
-    const bool interior = (s + 32 * RT * (rg + 1) <= k) && (l0 + 4 <= k);  // warp-uniform
-    const double *pv = V, *pw = W;
-    if (interior) {
-      for (int t = 0; t < pb; ++t, pv += kv, pw += kv) {
-        double vr[RT], wr[RT], vl[4], wl[4];
+      for (int J = 0; J < 4; ++J) acc[I][J][0] = acc[I][J][1] = 0.0;
+    int ro[4], lo[4];
 #pragma unroll
-        for (int a = 0; a < RT; ++a) {
-          vr[a] = pv[R0 + 32 * a];
-          wr[a] = pw[R0 + 32 * a];
+    for (int I = 0; I < 4; ++I) {
+      const int r = r0 + 8 * I + lr, l = l0 + 8 * I + lr;
+      ro[I] = interior ? r : (r < k ? r : k - 1);
+      lo[I] = interior ? l : (l < k ? l : k - 1);
+    }
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const double *P = VW + (half ? nb * kv : 0) + lc * kv, *Q = VW + (half ? 0 : nb * kv) + lc * kv;
+      for (int t0 = 0; t0 < pb4; t0 += 4, P += 4 * kv, Q += 4 * kv) {
+        double a[4], b[4];
+#pragma unroll
+        for (int I = 0; I < 4; ++I) {
+          a[I] = P[ro[I]];
+          b[I] = Q[lo[I]];
         }
 #pragma unroll
-        for (int b = 0; b < 4; ++b) {
-          vl[b] = pv[l0 + b];
-          wl[b] = pw[l0 + b];
-        }
+        for (int I = 0; I < 4; ++I)
 #pragma unroll
-        for (int a = 0; a < RT; ++a)
-#pragma unroll
-          for (int b = 0; b < 4; ++b) acc[a][b] = fma(vr[a], wl[b], fma(wr[a], vl[b], acc[a][b]));
+          for (int J = 0; J < 4; ++J) dmma884f(acc[I][J][0], acc[I][J][1], a[I], b[J]);
       }
+    }
 #pragma unroll
-      for (int b = 0; b < 4; ++b) {
-        AP col = A + (size_t)(l0 + b) * ld + R0;
+    for (int J = 0; J < 4; ++J) {
+      const int col = l0 + 8 * J + 2 * lc;
 #pragma unroll
-        for (int a = 0; a < RT; ++a) col[32 * a] -= acc[a][b];
+      for (int I = 0; I < 4; ++I) {
+        const int row = r0 + 8 * I + lr;
+        if (interior || (row < k && col < k)) A[row + (size_t)col * ld] -= acc[I][J][0];
+        if (interior || (row < k && col + 1 < k)) A[row + (size_t)(col + 1) * ld] -= acc[I][J][1];
       }
-    } else {
-      for (int t = 0; t < pb; ++t, pv += kv, pw += kv) {
-        double vr[RT], wr[RT], vl[4], wl[4];
-#pragma unroll
-        for (int a = 0; a < RT; ++a) {
-          const int r = R0 + 32 * a;
-          vr[a] = r < k ? pv[r] : 0.0;
-          wr[a] = r < k ? pw[r] : 0.0;
-        }
-#pragma unroll
-        for (int b = 0; b < 4; ++b) {
-          vl[b] = l0 + b < k ? pv[l0 + b] : 0.0;
-          wl[b] = l0 + b < k ? pw[l0 + b] : 0.0;
-        }
-#pragma unroll
-        for (int a = 0; a < RT; ++a)
-#pragma unroll
-          for (int b = 0; b < 4; ++b) acc[a][b] = fma(vr[a], wl[b], fma(wr[a], vl[b], acc[a][b]));
-      }
-#pragma unroll
-      for (int a = 0; a < RT; ++a)
-#pragma unroll
-        for (int b = 0; b < 4; ++b) {
-          const int r = R0 + 32 * a, l = l0 + b;
-          if (r < k && l < k) A[r + (size_t)l * ld] -= acc[a][b];
-        }
     }
   }
 }
@@ -176,7 +166,7 @@ enum { VK_NONE = 0, VK_B = 1, VK_FIELD = 2, VK_WBAR = 3, VK_UNIT = 4 };
 struct FcnSmem {
   int kp, nw, part_len, a_len, vw_len, wscr_len, total;
   __host__ __device__ FcnSmem(int k, int nw_, bool a_smem) {
-    kp = (k + 3) & ~3;
+    kp = ((k + 15) & ~15) + 4;  // row stride of V, W: 4 (mod 16) doubles (conflict-free mma fragment loads)
     nw = nw_;
     part_len = nw * 4 * 32;
     a_len = a_smem ? k * k : 0;
@@ -322,15 +312,18 @@ __global__ void __launch_bounds__(256, ASMEM ? 1 : 2)
       }
       __syncthreads();
     }
-    // trailing update with this panel
+    // trailing update with this panel (FP64 tensor pipe)
     {
-      const int s = c0 + pb, ntr = k - s;
-      if (ntr > 64)
-        trailing_update<4>(A, ld, k, s, pb, V, W, kp, warp, lane, nw);
-      else if (ntr > 32)
-        trailing_update<2>(A, ld, k, s, pb, V, W, kp, warp, lane, nw);
-      else
-        trailing_update<1>(A, ld, k, s, pb, V, W, kp, warp, lane, nw);
+      const int s = c0 + pb;
+      const int pb4 = (pb + 3) & ~3;
+      if (pb4 != pb) {  // last panel: rows [pb, pb4) of V and W still hold the previous panel
+        for (int x = tid; x < (pb4 - pb) * kp; x += nt) {
+          V[pb * kp + x] = 0.0;
+          W[pb * kp + x] = 0.0;
+        }
+        __syncthreads();
+      }
+      trailing_update_dmma(A, ld, k, s, pb, VW, kp, nb, warp, lane, nw);
     }
     __syncthreads();
   }

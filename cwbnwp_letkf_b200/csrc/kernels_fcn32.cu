@@ -9,6 +9,8 @@
 // Then the 32 pole solves of T^(-1/2) z run one per lane (pole_solve), and the epilogue of letkf_solve
 // (core:671-698) follows while everything is still on chip: per unit the kernel reads C (8 KB), b and the
 // field column, and writes the field column.
+#include <cstdlib>
+
 #include "fcn_common.cuh"
 
 namespace lk {
@@ -252,11 +254,22 @@ void launch_fcn32_solve(cudaStream_t s, const FcnArgs &a) {
   if (a.nunits == 0) return;
   LK_REQUIRE(a.k == 32, "fcn32: k must be 32");
   const size_t smem = sizeof(double) * 4 * SM_WARP;
-  auto kern = fcn32_kernel<3>;
-  LK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  static const int minb = [] {
+    const char *e = getenv("LETKF_B200_FCN32_MINB");  // resident CTAs per SM the kernel is compiled for (tuning knob)
+    return e ? atoi(e) : 3;
+  }();
   const int64_t nblk = (a.nunits + 3) / 4;
   LK_REQUIRE(nblk < ((int64_t)1 << 31), "fcn32: too many units for one launch");
-  kern<<<(unsigned)nblk, 128, smem, s>>>(a);
+  auto launch = [&](auto kern) {
+    LK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<(unsigned)nblk, 128, smem, s>>>(a);
+  };
+  if (minb == 4)
+    launch(fcn32_kernel<4>);
+  else if (minb == 5)
+    launch(fcn32_kernel<5>);
+  else
+    launch(fcn32_kernel<3>);
   LK_CUDA(cudaGetLastError());
 }
 

@@ -29,6 +29,7 @@ from typing import Callable, Dict, Iterable, Optional
 
 import numpy as np
 
+from . import config as C
 from . import partition
 
 G = np.float32(9.81)  # module_param.f90:109
@@ -92,15 +93,41 @@ def ensemble_mean_height(ph: np.ndarray, vstag: int) -> np.ndarray:
     return ((tmp[:, :, 1:] + tmp[:, :, :-1]) * np.float32(0.5)).astype(np.float32)
 
 
+def group_variables(var_update: Iterable[str], namelist: Callable[[str], object], batch: bool = True):
+    """var_update (core:59-61: the list ends at the first blank entry) split into runs of CONSECUTIVE variables
+    that letkf_driver would analyse with identical settings -- same stagger, same tune_q rule and a bit-identical
+    namelist slice (types, hclr/vclr, errors, inflation, RTPP/RTPS).  Such variables have the same local
+    observations and the same weights at every grid point, so one pass with nfields = len(group) replaces
+    len(group) passes.  With input.nml this groups the eight hydrometeor variables QRAIN .. QNHAIL."""
+    groups, prev = [], None
+    for name in var_update:
+        name = name.strip()
+        if not name:
+            break
+        if name not in VARIABLES:
+            raise ValueError("Need to code for unknown variable %s" % name)  # core:159-161
+        cfg = namelist(name)
+        saved, cfg.tune_q = cfg.tune_q, False
+        sig = (VARIABLES[name][1:], bytes(C.to_c(cfg)))
+        cfg.tune_q = saved
+        if batch and prev == sig and name != "MU":
+            groups[-1].append(name)
+        else:
+            groups.append([name])
+        prev = sig
+    return groups
+
+
 class LetkfDriver:
     """``run(wrf, var_update)`` == the ``update`` loop of letkf_driver for this rank."""
 
     def __init__(self, backend, namelist: Callable[[str], object], proj: Projection, rank: int = 0, world: int = 1,
-                 nxb: int = 1, nyb: int = 1):
+                 nxb: int = 1, nyb: int = 1, batch: bool = True):
         self.backend = backend          # .analyze(cfg, xyz[npts,3], var[k,npts]) and .tune_q(var[k,npts])
         self.namelist = namelist        # variable name -> VarConfig (module_config.f90:7-75)
         self.proj = proj
         self.rank, self.world, self.nxb, self.nyb = rank, world, nxb, nyb
+        self.batch = batch              # analyse variables with identical settings in one call (nfields > 1)
         self.log = []
 
     @staticmethod
@@ -116,27 +143,19 @@ class LetkfDriver:
         loc_nx, loc_ny = len(xloc), len(yloc)
         hstag, vstag = 0, 0                      # core:57-58
         lat = lon = alt = None
-        for name in var_update:
-            name = name.strip()
-            if not name:
-                break                            # core:61
-            if name not in VARIABLES:
-                raise ValueError("Need to code for unknown variable %s" % name)  # core:159-161
+        for group in group_variables(var_update, self.namelist, batch=self.batch):
+            name = group[0]
             key, hs, vs, is_q = VARIABLES[name]
             cfg = self.namelist(name)
             if not self._uses_any_tree(cfg):
-                self.log.append((name, "skipped: no observation type localises this variable"))
+                for nm in group:
+                    self.log.append((nm, "skipped: no observation type localises this variable"))
                 continue                         # core:66
             vnz = nz + 1 if vs == 1 else (1 if vs == -1 else nz)          # core:79-82
             xi = tab["xloc_u"] if hs == 1 else xloc                       # core:71-78
             yj = tab["yloc_v"] if hs == 2 else yloc
-            field = wrf[key]
-            if name == "MU":
-                field = field[:, :, None, :]     # core:142-146
             hreset, hstag = hstag != hs, hs      # check_coordinate
             vreset, vstag = vstag != vs, vs
-            var = np.ascontiguousarray(field[np.ix_(xi, yj)])              # letkf_scatter_grid, [lx, ly, vnz, k]
-            assert var.shape[2] == vnz
             if lat is None or hreset:            # core:165-186
                 sfx = {0: "", 1: "_u", 2: "_v"}[hs]
                 lat = wrf["xlat" + sfx][np.ix_(xi, yj)]
@@ -152,7 +171,19 @@ class LetkfDriver:
             xyz[..., 0] = x.T[None]
             xyz[..., 1] = y.T[None]
             xyz[..., 2] = np.transpose(alt[:, :, :vnz], (2, 1, 0))
-            work = np.ascontiguousarray(np.transpose(var[:loc_nx, :loc_ny], (3, 2, 1, 0))).reshape(var.shape[3], -1)
+            # letkf_scatter_grid for every variable of the group: [lx, ly, vnz, k] each
+            vars_, works = [], []
+            for nm in group:
+                field = wrf[VARIABLES[nm][0]]
+                if nm == "MU":
+                    field = field[:, :, None, :]     # core:142-146
+                var = np.ascontiguousarray(field[np.ix_(xi, yj)])
+                assert var.shape[2] == vnz
+                vars_.append(var)
+                works.append(np.ascontiguousarray(np.transpose(var[:loc_nx, :loc_ny], (3, 2, 1, 0))).reshape(var.shape[3], -1))
+            # variables with identical localisation / inflation share one set of weights per grid point:
+            # one call with nfields = len(group) (the eight hydrometeor variables of input.nml:7,37-38,162)
+            work = works[0] if len(group) == 1 else np.ascontiguousarray(np.stack(works, 0))
             if hasattr(self.backend, "set_levels"):
                 # declare the level count: when every active type is 2-D localised the library solves once
                 # per column and all levels share the weights (letkf_b200_set_levels)
@@ -163,11 +194,16 @@ class LetkfDriver:
             stats = self.backend.analyze(cfg, xyz.reshape(-1, 3), work)
             if hasattr(self.backend, "set_levels"):
                 self.backend.set_levels(1)
-            if is_q and not fused_q:
-                assert var.shape[:2] == (loc_nx, loc_ny)   # q variables are unstaggered
-                self.backend.tune_q(work)        # core:252-278: the whole local array
-            var[:loc_nx, :loc_ny] = np.transpose(work.reshape(var.shape[3], vnz, loc_ny, loc_nx), (3, 2, 1, 0))
-            out = wrf[key][:, :, None, :] if name == "MU" else wrf[key]
-            out[np.ix_(xi, yj)] = var            # letkf_gather_grid (this rank's columns)
-            self.log.append((name, stats))
+            for gi, nm in enumerate(group):
+                var = vars_[gi]
+                w = work if len(group) == 1 else work[gi]
+                if is_q and not fused_q:
+                    assert var.shape[:2] == (loc_nx, loc_ny)   # q variables are unstaggered
+                    w = np.ascontiguousarray(w)
+                    self.backend.tune_q(w)       # core:252-278: the whole local array
+                var[:loc_nx, :loc_ny] = np.transpose(w.reshape(var.shape[3], vnz, loc_ny, loc_nx), (3, 2, 1, 0))
+                k_ = VARIABLES[nm][0]
+                out = wrf[k_][:, :, None, :] if nm == "MU" else wrf[k_]
+                out[np.ix_(xi, yj)] = var        # letkf_gather_grid (this rank's columns)
+                self.log.append((nm, stats))
         return self.log

@@ -1,11 +1,10 @@
 #!/bin/bash
-# ncu --set full of fcn_blk_kernel on small grids (every replay pass saves / restores the C matrices the
-# kernel overwrites: keep them small).  Usage: profiles/ncu_fcn_blk.sh <tag>
+# ncu --set full of fcn_blk_kernel on a small grid (every replay pass saves / restores the C matrices the
+# kernel overwrites: keep them small).  Usage: profiles/ncu_fcn_blk.sh <tag> [members] [nx]
 set -e
 TAG=${1:-r02_fcnblk}
-CMD1="python bench.py --members 256 --steps 1 --warmup 1 --nx 12 --ny 12 --nz 20 --no-cpu-baseline --no-e2e"
-CMD2="python bench.py --members 96 --steps 1 --warmup 1 --nx 32 --ny 32 --nz 20 --no-cpu-baseline --no-e2e"
-$CMD1 > gpurun_out/${TAG}_k256_plain.json 2> gpurun_out/${TAG}_k256_plain.err
-ncu --set full --clock-control none --import-source on -k regex:"fcn_blk_kernel" -s 1 -c 1 -o gpurun_out/${TAG}_k256 -f $CMD1 > gpurun_out/${TAG}_k256_ncu.log 2>&1
-$CMD2 > gpurun_out/${TAG}_k96_plain.json 2> gpurun_out/${TAG}_k96_plain.err
-ncu --set full --clock-control none --import-source on -k regex:"fcn_blk_kernel|gram_tma_kernel" -s 2 -c 2 -o gpurun_out/${TAG}_k96 -f $CMD2 > gpurun_out/${TAG}_k96_ncu.log 2>&1
+K=${2:-256}
+NX=${3:-12}
+CMD1="python bench.py --members $K --steps 1 --warmup 1 --nx $NX --ny $NX --nz 20 --no-cpu-baseline --no-e2e --no-secondary"
+$CMD1 > gpurun_out/${TAG}_k${K}_plain.json 2> gpurun_out/${TAG}_k${K}_plain.err
+ncu --set full --clock-control none --import-source on -k regex:"fcn_blk_kernel" -s 1 -c 1 -o gpurun_out/${TAG}_k${K} -f $CMD1 > gpurun_out/${TAG}_k${K}_ncu.log 2>&1
