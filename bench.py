@@ -58,6 +58,9 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-secondary", action="store_true", help="skip the config L / config E block")
+    ap.add_argument("--workload", default="T", choices=["T", "cycle16"],
+                    help="T: the hot path over one 3-D variable (BASELINE config M, the headline); cycle16: one full "
+                         "analysis cycle of all 16 variables from host buffers incl. the field exchange (bench_cycle.py)")
     ap.add_argument("--parity-points", type=int, default=256,
                     help="points of the cpu_baseline sample on which lists / rows / weights are compared")
     ap.add_argument("--nxb", type=int, default=0,
@@ -327,6 +330,24 @@ def main():
               "partition": "1 GPU" if world == 1 else
               "columns block-cyclic (nxb=%d, nyb=%d) over a %dx%d process grid, obs replicated" %
               ((a.nxb, a.nyb) + P.process_grid(world))}
+
+    if a.workload == "cycle16":
+        import bench_cycle
+        if a.impl == "reference":
+            if rank == 0:
+                print(json.dumps(bench_cycle.run_reference(a)))
+            return
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        if world > 1:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        out = bench_cycle.run(a, rank, world, local_rank, ClockSampler)
+        if rank == 0:
+            print(json.dumps(out))
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     if a.impl == "reference":
         if rank != 0:

@@ -8,6 +8,8 @@ from oracle import oracle as O
 
 PROJ = dict(cen_lat=23.5, truelat1=10.0, truelat2=40.0, sta_lon=120.5)
 VARS = ["U", "V", "W", "T", "QVAPOR", "QRAIN", "P", "MU", "PH"]
+VARS_ALL = list(C.VAR_UPDATE)            # input.nml:7: all 16, the 8 hydrometeor variables share one configuration
+KEYS_ALL = ("u", "v", "w", "t", "qv", "qr", "qs", "qg", "qh", "nqr", "nqs", "nqg", "nqh", "p", "mu", "ph")
 
 
 def inverse_projection(p: D.Projection, x, y):
@@ -60,6 +62,10 @@ def make_state(k=8, nx=9, ny=8, nz=5, dx=3000.0, seed=11):
     qr = np.abs(fld((nx, ny, nz), 1e-4, 3e-4))
     qr[rng.random(qr.shape) < 0.3] = 0.0
     wrf["qr"] = qr
+    for i, key in enumerate(("qs", "qg", "qh", "nqr", "nqs", "nqg", "nqh")):   # the other hydrometeor variables
+        q2 = np.abs(fld((nx, ny, nz), 1e-4 * (i + 1), 3e-4))
+        q2[rng.random(q2.shape) < 0.3] = 0.0
+        wrf[key] = q2
     return sc, wrf, proj
 
 

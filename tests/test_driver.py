@@ -165,3 +165,22 @@ def test_driver_skips_variable_without_trees(case):
     assert np.array_equal(st["t"], wrf["t"])
     with pytest.raises(ValueError):
         D.LetkfDriver(OracleBackend(sc), namelist, proj).run(copy_state(wrf), ["QCLOUD"])
+
+
+def test_batched_hydrometeor_pass_equals_single_variable_passes(case):
+    """The eight hydrometeor variables of input.nml share their configuration: one pass with nfields = 8
+    (driver.group_variables) gives bit-identical fields to eight passes (core:59-297 analyses them one by one)."""
+    from _driver_case import KEYS_ALL, VARS_ALL
+    sc, wrf, proj = case[:3]
+    backend = OracleBackend(sc)
+    groups = D.group_variables(VARS_ALL, namelist)
+    assert [len(g) for g in groups] == [1, 1, 1, 1, 1, 8, 1, 1, 1]
+    a, b = copy_state(wrf), copy_state(wrf)
+    la = D.LetkfDriver(backend, namelist, proj, batch=True).run(a, VARS_ALL)
+    lb = D.LetkfDriver(backend, namelist, proj, batch=False).run(b, VARS_ALL)
+    assert [n for n, _ in la] == [n for n, _ in lb] == VARS_ALL
+    for key in KEYS_ALL:
+        assert np.array_equal(np.isnan(a[key]), np.isnan(b[key])), key
+        ok = ~np.isnan(a[key])
+        assert np.array_equal(a[key][ok], b[key][ok]), key
+    assert any((a[k_] != wrf[k_])[~np.isnan(a[k_])].any() for k_ in ("qs", "nqh"))
