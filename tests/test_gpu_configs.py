@@ -152,10 +152,11 @@ def test_config_3D_all_types_vertical_localisation():
 
 
 # ------------------------------------------------------------------------------------------- odd member counts
-@pytest.mark.parametrize("k", [30, 50, 99])
+@pytest.mark.parametrize("k", [30, 50, 99, 170, 250])
 def test_member_counts_not_multiple_of_4_with_many_rows(k):
     """k % 4 != 0 takes gram_dmma_kernel (no TMA row gather); radar-dense points give p >> k, several row
-    batches and super-blocks."""
+    batches and super-blocks.  170 and 250 are member counts the round-1 FP64 solver refused (k > 160 had to be a
+    multiple of 32); the reference takes any nmember (module_eigen.f90:16-35, input.nml:6)."""
     sc, rng = S.scenario_tiny(k=k, n_dbz=3000, n_vr=2500)
     cfg = C.sample_namelist("T")
     eng, orc = _engines(sc)
