@@ -201,6 +201,13 @@ def stage_report(stats, k: int, fma64: float, members: int):
     except Exception:
         tt = {}
     tab = tt.get("k%d" % members, {})
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        from tree_stamp import tree_stamp
+        if tt.get("stamp") != tree_stamp():
+            tab = {}            # the committed capture is from another tree: its numbers are not this run's
+    except Exception:
+        tab = {}
     per_launch_units = min(units, 1 << 18)
     for s_ in ("search", "gram", "solve"):
         t_ = tab.get(s_)

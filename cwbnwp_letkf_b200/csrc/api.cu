@@ -79,7 +79,17 @@ static int guarded(F &&f) {
 template <typename F>
 static int guarded(letkf_b200_ctx *c, F &&f) {
   CtxBind bind(c);
-  return guarded(std::forward<F>(f));
+  const int rc = guarded(std::forward<F>(f));
+  if (rc != 0 && c) {
+    // a failed call must not leave copies in flight on the caller's arrays (the Fortran shim stops the
+    // program and may deallocate them): drain the compute and the two copy streams before returning
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->cs_in) cudaStreamSynchronize(c->cs_in);
+    if (c->cs_out) cudaStreamSynchronize(c->cs_out);
+    cudaGetLastError();
+  }
+  return rc;
 }
 
 extern "C" const char *letkf_b200_last_error(void) { return g_last_error.c_str(); }
@@ -479,12 +489,6 @@ static void run_pipeline(letkf_b200_ctx *c, const letkf_b200_var_config *cfg, in
                           !co.Wa && eig32_can_fuse();
         Xform32Args xargs{c->unit_pt.p, c->nanflag.p, npts, c0, nfields, d_var, cfg->use_rtpp, cfg->rtpp_alpha,
                           cfg->use_rtps, cfg->rtps_alpha, co.xa_raw};
-        if (fuse && letkf32_fuse_all()) {
-          // everything after the search in one kernel (Gram on the tensor pipe overlaps Jacobi on the FP64 pipe)
-          launch_letkf32_fused(s, tv, nunits, (double)mu, xargs, c->counters.p + 1);
-          LK_CUDA(cudaEventRecord(c->ev[4], s));
-          LK_CUDA(cudaEventRecord(c->ev[5], s));
-        } else {
         if (fast32 && sizeof(T) == 8)
           launch_gram32(s, tv, nunits, c->unit_pt.p, (double)mu, reinterpret_cast<double *>(C),
                         reinterpret_cast<double *>(b), c->nanflag.p);
@@ -558,7 +562,6 @@ static void run_pipeline(letkf_b200_ctx *c, const letkf_b200_var_config *cfg, in
           }
         }
         }
-        }
         LK_CUDA(cudaEventRecord(c->ev[6], s));
         if (host_io) chunk_out(ci, c0, nq, false);
         LK_CUDA(cudaEventSynchronize(c->ev[6]));
@@ -588,6 +591,8 @@ static void run_pipeline(letkf_b200_ctx *c, const letkf_b200_var_config *cfg, in
     LK_CUDA(cudaStreamSynchronize(s));
     stats.max_sweeps = h_sw[0];
     stats.sweeps_sum = h_sw[1];
+    LK_REQUIRE(h_sw[0] <= (k == 32 && !c->force_generic ? LK_JACOBI_CAP32 : LK_JACOBI_CAP),
+               "Jacobi eigensolver did not converge within its sweep cap: the analysis of this variable is invalid");
   }
   LK_CUDA(cudaEventRecord(c->ev[7], s));
   LK_CUDA(cudaEventSynchronize(c->ev[7]));
@@ -892,10 +897,12 @@ static void syevd_dev(letkf_b200_ctx *c, int k, int64_t batch, const void *A, vo
     launch_syevd32<T>(c->stream, batch, (const T *)A, (T *)W, (T *)V, c->counters.p + 1);
   else
     launch_syevd<T>(c->stream, k, batch, (const T *)A, (T *)W, (T *)V, c->counters.p + 1);
-  if (sweeps) {
-    LK_CUDA(cudaMemcpyAsync(sweeps, c->counters.p + 1, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
-    LK_CUDA(cudaStreamSynchronize(c->stream));
-  }
+  int32_t h_sw = 0;
+  LK_CUDA(cudaMemcpyAsync(&h_sw, c->counters.p + 1, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+  LK_CUDA(cudaStreamSynchronize(c->stream));
+  if (sweeps) *sweeps = h_sw;
+  LK_REQUIRE(h_sw <= (k == 32 && !c->force_generic ? LK_JACOBI_CAP32 : LK_JACOBI_CAP),
+             "syevd_batched: the Jacobi iteration did not converge within its sweep cap for at least one matrix");
 }
 
 extern "C" int letkf_b200_syevd_batched_dev(letkf_b200_ctx *c, int k, int64_t batch, int real64, const void *A,

@@ -244,7 +244,7 @@ __device__ int block_jacobi_rb(T *G, int k, int kp, int ld, int nrows, T *nrm, T
   auto colp = [&](int c) { return (MIXED && c < nres) ? R + (size_t)c * ldr : G + (size_t)c * ld; };
   auto cold = [&](int c) { return (MIXED && c < nres) ? ldr : ld; };
   int sweeps = 0;
-  for (; sweeps < 40; ++sweeps) {
+  for (; sweeps < LK_JACOBI_CAP; ++sweeps) {
     int rotated = 0, big = 0;
     // pass 1: pairs inside each block of 4 columns, plus exact column norms
     for (int I = warp; I < nb; I += nw)
@@ -262,12 +262,9 @@ __device__ int block_jacobi_rb(T *G, int k, int kp, int ld, int nrows, T *nrm, T
     }
     const int any_rot = __syncthreads_or(rotated);
     const int any_big = __syncthreads_or(big);
-    if (!any_rot || !any_big) {
-      ++sweeps;
-      break;
-    }
+    if (!any_rot || !any_big) return sweeps + 1;
   }
-  return sweeps;
+  return LK_JACOBI_CAP + 1;  // not converged: reported as an error by the caller (api.cu)
 }
 
 __device__ __forceinline__ void dmma884b(double &d0, double &d1, double a, double b) {

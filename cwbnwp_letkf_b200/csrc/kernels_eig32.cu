@@ -18,12 +18,12 @@
 #include <cstdlib>
 
 #include "eig_common.cuh"
-#include "gram32.cuh"
 #include "xform32.cuh"
 
 namespace lk {
 
 constexpr int K32 = 32;
+constexpr int JACOBI32_CAP = 30;  // == LK_JACOBI_CAP32 (letkf_internal.cuh)
 constexpr unsigned FULL = 0xffffffffu;
 
 __host__ __device__ constexpr int rr_pos(int m) { return (m & 1) ? 31 - (m >> 1) : (m >> 1); }
@@ -96,7 +96,7 @@ __device__ __forceinline__ int warp_jacobi32(T (&g)[K32], int lane, T *csbuf, T 
   const int src_lane = pp <= 15 ? 2 * pp : 2 * (31 - pp) + 1;
   const T *mypart = part + (lane >> 1) * 32 + (lane & 1) * 16;
   int sweeps = 0;
-  for (; sweeps < 30; ++sweeps) {
+  for (; sweeps < JACOBI32_CAP; ++sweeps) {
     // exact squared column norms: lane l <- ||column in register slot l||^2
     T d;
     {
@@ -156,12 +156,9 @@ __device__ __forceinline__ int warp_jacobi32(T (&g)[K32], int lane, T *csbuf, T 
       d = __shfl_sync(FULL, d, src_lane);
       __syncwarp();  // csbuf / part are rewritten by the next step
     }
-    if (!__any_sync(FULL, rotated) || !__any_sync(FULL, big)) {
-      ++sweeps;
-      break;
-    }
+    if (!__any_sync(FULL, rotated) || !__any_sync(FULL, big)) return sweeps + 1;
   }
-  return sweeps;
+  return JACOBI32_CAP + 1;  // not converged: reported as an error by the caller (api.cu)
 }
 
 // MODE 0: C (row-major lower / symmetric full, SPD), b -> U^T-by-rows (U[i][j] at i*32+j), lam, wbar
@@ -343,15 +340,10 @@ __device__ __forceinline__ void warp_gemm32_dmma(FA fa, FB fb, double *out, int 
   __syncwarp();
 }
 
-// GRAM = true is the fully fused per-unit pipeline: the warp first accumulates its own C and b on the
-// tensor pipe (gram32_unit, straight into shared memory), then solves and transforms.  Warps of an SM
-// are at different phases, so Gram work (tensor pipe) of some warps overlaps the Jacobi work (FP64
-// pipe, latency bound) of the others, and C / U never touch global memory.
-template <bool GRAM>
 __global__ void __launch_bounds__(128, 3)
     eig32_chain_kernel(int RUN, int64_t n, double *__restrict__ Cio, const double *__restrict__ bvec,
                        double *__restrict__ lam, double *__restrict__ wbar, int32_t *__restrict__ sweeps_max,
-                       int32_t *__restrict__ sweeps_sum, bool fused, Xform32Args xa, TreeViews tv, double mu) {
+                       int32_t *__restrict__ sweeps_sum, bool fused, Xform32Args xa) {
   using T = double;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -366,16 +358,11 @@ __global__ void __launch_bounds__(128, 3)
   bool prev_ok = false;
   for (int64_t u = u0; u < u1; ++u) {
     const bool warm = prev_ok;
-    const T *Cu = GRAM ? Bbuf : Cio + u * (int64_t)(K32 * K32);
-    const int ldc = GRAM ? LDA32 : K32;
-    bool nan_unit = false;
-    if (GRAM) {
-      nan_unit = gram32_unit(tv, xa.unit_pt[u], mu, Bbuf, LDA32, cs + 32, lane);
-      __syncwarp();
-    }
+    const T *Cu = Cio + u * (int64_t)(K32 * K32);
+    const int ldc = K32;
     T g[K32];
     if (warm) {
-      // T = C U_prev  (C from global memory, L1/L2 resident, or from shared memory when GRAM)
+      // T = C U_prev  (C from global memory, L1/L2 resident)
       warp_gemm32_dmma([&](int r, int c) { return Cu[r * ldc + c]; },
                        [&](int r, int c) { return Abuf[r * LDA32 + c]; }, Bbuf, lane);
       // C' = U_prev^T T   (written over T)
@@ -427,7 +414,7 @@ __global__ void __launch_bounds__(128, 3)
     // not seed its neighbour
     prev_ok = !__any_sync(FULL, !(lambda > T(0)) || !(lambda < T(1e300)));
     // wbar = U diag(1/lambda) U^T b
-    const T bi = GRAM ? cs[32 + lane] : bvec[u * K32 + lane];
+    const T bi = bvec[u * K32 + lane];
     T z;
     {
       T pr[K32];
@@ -442,10 +429,10 @@ __global__ void __launch_bounds__(128, 3)
 #pragma unroll
     for (int j = 0; j < K32; ++j) wb = fma(g[j], cs[j], wb);
     __syncwarp();
-    if (fused || GRAM) {
+    if (fused) {
       // transform the fields right here: U never goes to memory (saves 16 KB of traffic per unit)
       const T scale = sqrt((T)31) * Fast<T>::rsqrt(lambda);
-      const bool isnan_unit = GRAM ? nan_unit : xa.nanflag[u] != 0;
+      const bool isnan_unit = xa.nanflag[u] != 0;
       transform32_unit<T>(g, scale, wb, isnan_unit, xa.pt_base + xa.unit_pt[u], xa, cs, lane);
     } else {
       T *Uo = Cio + u * (int64_t)(K32 * K32) + (int64_t)lane * K32;
@@ -477,7 +464,7 @@ void launch_eig32_solve(cudaStream_t s, int64_t n, T *C_inout_U, const T *b, T *
   if (chain > 1 && sizeof(T) == 8) {
     const int RUN = chain;
     const size_t smem = sizeof(double) * 4 * (2 * 32 * LDA32 + 64);
-    auto kern = eig32_chain_kernel<false>;
+    auto kern = eig32_chain_kernel;
     LK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t nwarp = (n + RUN - 1) / RUN;
     kern<<<(unsigned)((nwarp + 3) / 4), 128, smem, s>>>(RUN, n, reinterpret_cast<double *>(C_inout_U),
@@ -485,7 +472,7 @@ void launch_eig32_solve(cudaStream_t s, int64_t n, T *C_inout_U, const T *b, T *
                                                          reinterpret_cast<double *>(lam),
                                                          reinterpret_cast<double *>(wbar), sweeps_max,
                                                          sweeps_max ? sweeps_max + 1 : nullptr, fuse != nullptr,
-                                                         fuse ? *fuse : Xform32Args{}, TreeViews{}, 0.0);
+                                                         fuse ? *fuse : Xform32Args{});
     launch_counter()++;
     LK_CUDA(cudaGetLastError());
     return;
@@ -512,28 +499,6 @@ template void launch_eig32_solve<double>(cudaStream_t, int64_t, double *, const 
                                          int32_t *, const Xform32Args *);
 template void launch_eig32_solve<float>(cudaStream_t, int64_t, float *, const float *, float *, float *, int32_t *,
                                         const Xform32Args *);
-// Fully fused k = 32 FP64 pipeline for one chunk: Gram + eigen + transform in one kernel.
-void launch_letkf32_fused(cudaStream_t s, const TreeViews &tv, int64_t n, double mu, const Xform32Args &xa,
-                          int32_t *sweeps_max) {
-  if (n == 0) return;
-  const int RUN = 16;
-  const size_t smem = sizeof(double) * 4 * (2 * 32 * LDA32 + 64);
-  auto kern = eig32_chain_kernel<true>;
-  LK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int64_t nwarp = (n + RUN - 1) / RUN;
-  kern<<<(unsigned)((nwarp + 3) / 4), 128, smem, s>>>(RUN, n, nullptr, nullptr, nullptr, nullptr, sweeps_max,
-                                                       sweeps_max ? sweeps_max + 1 : nullptr, true, xa, tv, mu);
-  launch_counter()++;
-  LK_CUDA(cudaGetLastError());
-}
-// Off by default: measured on config M the fully fused kernel takes 1435 ms against 441 + 719 ms for
-// the separate Gram and eigen kernels -- at the eigensolver's occupancy (12 warps/SM, 168 registers)
-// the Gram phase is latency bound and the hoped-for tensor/FP64 pipe overlap does not pay for it.
-bool letkf32_fuse_all() {
-  const char *f = getenv("LETKF_B200_FUSE_ALL");
-  return f && atoi(f) != 0;
-}
-
 bool eig32_can_fuse() {
   const char *e = getenv("LETKF_B200_EIG_CHAIN");
   const char *f = getenv("LETKF_B200_FUSE");

@@ -186,10 +186,6 @@ template <typename T>
 void launch_eig32_solve(cudaStream_t s, int64_t n, T *C_inout_U, const T *b, T *lam, T *wbar, int32_t *sweeps_max,
                         const Xform32Args *fuse);
 bool eig32_can_fuse();
-// k = 32 FP64: Gram + eigen + transform of a chunk in ONE kernel (C, U stay on chip)
-void launch_letkf32_fused(cudaStream_t s, const TreeViews &tv, int64_t n, double mu, const Xform32Args &xa,
-                          int32_t *sweeps_max);
-bool letkf32_fuse_all();
 template <typename T>
 void launch_syevd32(cudaStream_t s, int64_t n, const T *A, T *W, T *V, int32_t *sweeps_max);
 template <typename T>
@@ -235,5 +231,8 @@ struct CtxShared {
 };
 CtxShared *&current_ctx_shared();
 int64_t &launch_counter();
+
+// sweep caps of the Jacobi eigensolvers; a kernel reports cap + 1 when the stop criterion was not met
+constexpr int LK_JACOBI_CAP = 40, LK_JACOBI_CAP32 = 30;
 
 }  // namespace lk

@@ -97,6 +97,27 @@ module letkf_b200
             type(letkf_b200_stats),      intent(out)   :: stats
             integer(c_int)                             :: rc
         end function
+        ! npts = ncol*nz with levels slowest: 2-D localised variables then share weights per column
+        function letkf_b200_set_levels(ctx, nz) bind(C, name="letkf_b200_set_levels") result(rc)
+            import :: c_ptr, c_int
+            type(c_ptr),    value :: ctx
+            integer(c_int), value :: nz
+            integer(c_int)        :: rc
+        end function
+        ! CUDA runtime: page-lock the work arrays so that the library's asynchronous chunk copies overlap the
+        ! analysis (pageable memory works too, but serialises them); flags = 0 (cudaHostRegisterDefault)
+        function cudaHostRegister(ptr, nbytes, flags) bind(C, name="cudaHostRegister") result(rc)
+            import :: c_ptr, c_int, c_size_t
+            type(c_ptr),       value :: ptr
+            integer(c_size_t), value :: nbytes
+            integer(c_int),    value :: flags
+            integer(c_int)           :: rc
+        end function
+        function cudaHostUnregister(ptr) bind(C, name="cudaHostUnregister") result(rc)
+            import :: c_ptr, c_int
+            type(c_ptr), value :: ptr
+            integer(c_int)     :: rc
+        end function
     end interface
 
 contains
@@ -242,6 +263,8 @@ contains
         real, dimension(2)                 :: xy
         integer                            :: i, j, k, m, n
         integer(c_int64_t)                 :: npts
+        logical                            :: pinned
+        integer(c_int)                     :: rc_unused
 
         call b200_make_config(ivar, is_q, cfg)
         npts = int(loc_nx, c_int64_t) * loc_ny * nz
@@ -261,7 +284,13 @@ contains
         end do
         end do
 
+        ! pinned work array: the fields then stream through the device chunk by chunk under the analysis
+        pinned = cudaHostRegister(c_loc(work), int(npts, c_size_t) * nmember * 4_c_size_t, 0_c_int) == 0
+        ! all levels of a column share (x, y): lets MU / P / PH (vclr <= 0 everywhere) solve once per column
+        call check(letkf_b200_set_levels(ctx, int(nz, c_int)))
         call check(letkf_b200_analyze(ctx, cfg, npts, c_loc(xyz), 1_c_int, c_loc(work), stats))
+        call check(letkf_b200_set_levels(ctx, 1_c_int))
+        if (pinned) rc_unused = cudaHostUnregister(c_loc(work))
 
         do m = 0, nmember-1
         do k = 1, nz

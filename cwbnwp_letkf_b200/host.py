@@ -112,6 +112,17 @@ def _np(a, dtype):
     return np.ascontiguousarray(a, dtype)
 
 
+def _sync_producer(*tensors):
+    """The *_dev entry points launch on the library's own stream (letkf_b200_stream): whatever produced the
+    caller's device buffers -- torch kernels, an NCCL collective -- must have completed first (contract stated in
+    include/letkf_b200.h).  The library's calls return only when their own work is complete."""
+    for t in tensors:
+        if t is not None and hasattr(t, "is_cuda") and t.is_cuda:
+            import torch
+            torch.cuda.current_stream(t.device).synchronize()
+            return
+
+
 def _ptr(a):
     if a is None:
         return None
@@ -178,6 +189,7 @@ class LetkfB200:
 
     def set_obs_dev(self, family, type_, n, nvar, xyz, obs, error, hdxb, qc):
         """Device-resident variant (torch CUDA tensors, same layouts)."""
+        _sync_producer(xyz, obs, error, hdxb, qc)
         self._chk(self.L.letkf_b200_set_obs_dev(self.h, family, type_, n, nvar, _ptr(xyz), _ptr(obs),
                                                 _ptr(error), _ptr(hdxb), _ptr(qc)))
 
@@ -206,6 +218,7 @@ class LetkfB200:
         nfields = 1 if var.dim() == 2 else var.shape[0]
         assert tuple(var.shape[-2:]) == (self.k, npts)
         cc, st = C.to_c(cfg), Stats()
+        _sync_producer(xyz_grid, var)
         self._chk(self.L.letkf_b200_analyze_dev(self.h, ctypes.byref(cc), npts, _ptr(xyz_grid), nfields,
                                                 _ptr(var), ctypes.byref(st)))
         self.last_stats = st
@@ -306,6 +319,7 @@ class LetkfB200:
         b, k, _ = A.shape
         import torch
         sw = ctypes.c_int32(0)
+        _sync_producer(A)
         self._chk(self.L.letkf_b200_syevd_batched_dev(self.h, k, b, int(A.dtype == torch.float64), _ptr(A),
                                                       _ptr(W), _ptr(V), ctypes.byref(sw)))
         return sw.value

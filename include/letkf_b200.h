@@ -17,7 +17,14 @@
  *   - arrays are Fortran column-major exactly as the reference declares them; indices
  *     returned to the caller are 1-based like kdtree2's.
  *   - functions ending in _dev take DEVICE pointers (data already resident in HBM);
- *     the others take HOST pointers and do their own transfers.  The caller owns every
+ *     the others take HOST pointers and do their own transfers.  STREAM ORDER: the library
+ *     launches on its own non-blocking stream (letkf_b200_stream); it does not wait for the
+ *     stream that produced a caller's device buffer.  The caller must synchronise its producing
+ *     stream (or make letkf_b200_stream wait on an event of it) before a _dev call.  Every call
+ *     returns only after its own device work has completed, so results may be consumed on any
+ *     stream afterwards.  Host arrays passed to letkf_b200_analyze are streamed with asynchronous
+ *     copies: page-locked (pinned) memory lets those copies overlap the analysis; pageable
+ *     arrays work but serialise them.  On failure all copies are drained before the call returns.  The caller owns every
  *     array it passes; the library keeps no host pointer after a call returns
  *     (set_obs copies to the device).
  *   - one call at a time per context (the reference hot path is non-reentrant too:
