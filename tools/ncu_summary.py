@@ -1,6 +1,6 @@
 #!/usr/bin/env python
-"""Summarise an .ncu-rep (read with `ncu -i ... --page raw --csv`): one dict per captured launch with the
-counters the roofline discussion uses.  Usage: tools/ncu_summary.py file.ncu-rep [out.json]"""
+"""Summarise an .ncu-rep (read with `ncu -i ... --page raw --csv`) or such a CSV export: one dict per captured
+launch with the counters the roofline discussion uses.  Usage: tools/ncu_summary.py file.ncu-rep|file.csv [out.json]"""
 import csv
 import io
 import json
@@ -47,7 +47,10 @@ KEYS = {
 
 def main():
     rep = sys.argv[1]
-    txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], stdout=subprocess.PIPE, text=True).stdout
+    if rep.endswith(".csv"):     # already exported with `ncu -i x.ncu-rep --page raw --csv`
+        txt = open(rep).read()
+    else:
+        txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], stdout=subprocess.PIPE, text=True).stdout
     rows = list(csv.reader(io.StringIO(txt)))
     hdr, units = rows[0], rows[1]
     out = []

@@ -22,7 +22,9 @@ def main():
     traffic = {"source": "profiles/regen.sh %s (ncu --set full --clock-control none, small cases)" % tag, "git": stamp,
                "stamp": stamp}
     for case in ("k32", "k256", "k96"):
-        rep = os.path.join(OUT, "%s_%s.ncu-rep" % (tag, case))
+        rep = os.path.join(OUT, "%s_%s_raw.csv" % (tag, case))
+        if not os.path.exists(rep):
+            rep = os.path.join(OUT, "%s_%s.ncu-rep" % (tag, case))
         if not os.path.exists(rep):
             continue
         summ = os.path.join(PROF, "%s_ncu_%s_summary.json" % (tag, case))
