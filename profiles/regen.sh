@@ -18,7 +18,7 @@ C96="$B --members 96 --nx 32 --ny 32 --nz 20"
 # ---- k = 32 (config M at 1/9 of the columns: one pipeline chunk = 2^18 units)
 $C32 > $OUT/${TAG}_k32_plain.json 2> $OUT/${TAG}_k32_plain.err
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/${TAG}_k32_launches.csv $C32 > $OUT/${TAG}_k32_ncu1.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:"search_kernel|gram32_dmma_kernel|fcn32_kernel|count_rows" -s 8 -c 7 -o $OUT/${TAG}_k32 -f $C32 > $OUT/${TAG}_k32_ncu.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"search_kernel|gram32_dmma_kernel|fcn32_kernel|count_rows" -s 8 -c 8 -o $OUT/${TAG}_k32 -f $C32 > $OUT/${TAG}_k32_ncu.log 2>&1
 # ---- k = 256 (config L)
 $C256 > $OUT/${TAG}_k256_plain.json 2> $OUT/${TAG}_k256_plain.err
 ncu --set full --clock-control none --import-source on -k regex:"gram_tma_kernel|fcn_blk_kernel" -s 2 -c 2 -o $OUT/${TAG}_k256 -f $C256 > $OUT/${TAG}_k256_ncu.log 2>&1
