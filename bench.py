@@ -58,6 +58,9 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-secondary", action="store_true", help="skip the config L / config E block")
+    ap.add_argument("--localization", default="nml", choices=["nml", "3d"],
+                    help="3d: BASELINE config 4 -- every active observation type localised in 3-D (vclr > 0; types "
+                         "that input.nml localises in 2-D get vclr = 3 km) with max_lz_pts = 300 (README TODO, SURVEY Q17)")
     ap.add_argument("--workload", default="T", choices=["T", "cycle16"],
                     help="T: the hot path over one 3-D variable (BASELINE config M, the headline); cycle16: one full "
                          "analysis cycle of all 16 variables from host buffers incl. the field exchange (bench_cycle.py)")
@@ -330,7 +333,13 @@ def main():
     cfg = C.sample_namelist(a.var)
     cfg.tune_q = False if a.var == "T" else cfg.tune_q
     cfg._name = a.var
-    workload = f"M: {a.nx}x{a.ny}x{a.nz} grid, dx=2km, k={a.members}, variable {a.var}"
+    if a.localization == "3d":
+        for t in cfg.types:
+            if t.use_it and t.hclr > 0:
+                t.vclr = t.vclr if t.vclr > 0 else 3.0
+                t.max_lz_pts = 300
+    workload = f"M: {a.nx}x{a.ny}x{a.nz} grid, dx=2km, k={a.members}, variable {a.var}" + \
+        (", 3-D localisation on every type, max_lz_pts 300 (config 3D)" if a.localization == "3d" else "")
     config = {"workload": workload, "members": a.members, "variable": a.var,
               "namelist": "input.nml (hclr/vclr/max_lz_pts/inflation/RTPP/RTPS as shipped)",
               "l2": "inputs larger than L2 (ensemble field %.2f GB)" % (a.nx * a.ny * a.nz * a.members * 4 / 1e9),
