@@ -3,10 +3,10 @@
 //   1. blocked Householder tridiagonalisation C = Q T Q^T (LAPACK dsytrd / dlatrd organisation: inside
 //      a panel of NB columns the trailing matrix is only READ -- one symmetric matrix-vector product per
 //      column, corrected with the panel's V, W -- and updated once per panel by the rank-2NB product
-//      A -= V W^T + W V^T on the FP64 tensor pipe).  The matrix lives in shared memory while two CTAs still
-//      fit on an SM (k <= ~88), otherwise in place in global memory (L2): its bytes are then streamed once
-//      per column instead of three times, and never more than 512 KB per CTA are live (the Jacobi path kept
-//      three such matrices per CTA).
+//      A -= V W^T + W V^T on the FP64 tensor pipe).  The matrix is processed in place in global memory and
+//      stays L2 resident: its bytes are streamed once per column instead of three times, never more than the
+//      k x k doubles of C are live per CTA (the Jacobi path kept three such matrices per CTA), and the small
+//      shared-memory footprint (panel + vectors) lets many CTAs share an SM.
 //      The reflectors overwrite the eliminated columns (as LAPACK stores them).
 //   2. spectrum bound (Gershgorin of T), pole table row q, LDL^T pivots of T + a beta_j I for the 32 poles.
 //   3. for every vector (b, the field perturbations of every level that shares the weights, unit
@@ -164,26 +164,25 @@ enum { VK_NONE = 0, VK_B = 1, VK_FIELD = 2, VK_WBAR = 3, VK_UNIT = 4 };
 
 // shared-memory layout (doubles), shared by the kernel and the host-side size computation
 struct FcnSmem {
-  int kp, nw, part_len, a_len, vw_len, wscr_len, total;
-  __host__ __device__ FcnSmem(int k, int nw_, bool a_smem) {
+  int kp, nw, part_len, vw_len, wscr_len, total;
+  __host__ __device__ FcnSmem(int k, int nw_) {
     kp = ((k + 15) & ~15) + 4;  // row stride of V, W: 4 (mod 16) doubles (conflict-free mma fragment loads)
     nw = nw_;
     part_len = nw * 4 * 32;
-    a_len = a_smem ? k * k : 0;
     vw_len = (2 * FCN_NB * kp > 32 * k) ? 2 * FCN_NB * kp : 32 * k;
     wscr_len = 3 * kp + (k / FCN_SEG + 1) * 32;  // zb[kp], xp[kp], f32 pair [kp], ck
-    total = 5 * kp + 4 * 32 + part_len + a_len + vw_len + FCN_NVW * wscr_len;
+    total = 5 * kp + 4 * 32 + part_len + vw_len + FCN_NVW * wscr_len;
   }
 };
 
-template <int RPL, bool ASMEM>
-__global__ void __launch_bounds__(256, ASMEM ? 1 : 2)
+template <int RPL>
+__global__ void __launch_bounds__(256, 2)
     fcn_blk_kernel(FcnArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int k = a.k;
   const int tid = threadIdx.x, nt = blockDim.x;
   const int warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
-  const FcnSmem L(k, nw, ASMEM);
+  const FcnSmem L(k, nw);
   const int kp = L.kp;  // padded vector length (row stride of V, W)
   const int nb = FCN_NB;
   double *sm = reinterpret_cast<double *>(smem_raw);
@@ -197,8 +196,7 @@ __global__ void __launch_bounds__(256, ASMEM ? 1 : 2)
   double *s1 = red2 + 32;         // [32]
   double *s2 = s1 + 32;           // [32]
   double *part = s2 + 32;         // [nw * 4 * 32]
-  double *As = part + L.part_len; // [k * k] when ASMEM (reads may run up to 127 rows past a column: VW follows)
-  double *VW = As + L.a_len;      // [2 * nb * kp], later rp[k * 32]
+  double *VW = part + L.part_len; // [2 * nb * kp], later rp[k * 32]
   double *wscr = VW + L.vw_len;   // FCN_NVW x per-warp scratch
   const int wscr_len = L.wscr_len;
   __shared__ int s_q;
@@ -207,19 +205,14 @@ __global__ void __launch_bounds__(256, ASMEM ? 1 : 2)
   const int64_t unit = blockIdx.x;
   if (unit >= a.nunits) return;
   double *Cg = a.C + unit * (int64_t)k * k;
-  double *A = ASMEM ? As : Cg;
+  double *A = Cg;  // processed in place in global memory: L2 resident (rows >= k of a column read the next column)
   const int ld = k;
   double *V = VW, *W = VW + (size_t)nb * kp;
 
   // ---- load / symmetrise (the Gram kernels deliver the column-major lower triangle) ----
   for (int x = tid; x < 2 * nb * kp; x += nt) VW[x] = 0.0;
   for (int j = warp; j < k; j += nw)
-    for (int i = lane; i < k; i += 32) {
-      if (ASMEM)
-        As[i + j * k] = i >= j ? Cg[i + (size_t)j * k] : Cg[j + (size_t)i * k];
-      else if (i < j)
-        Cg[i + (size_t)j * k] = Cg[j + (size_t)i * k];
-    }
+    for (int i = lane; i < j; i += 32) Cg[i + (size_t)j * k] = Cg[j + (size_t)i * k];
   __syncthreads();
 
   // ---- 1. tridiagonalisation ----
@@ -501,48 +494,33 @@ __global__ void __launch_bounds__(256, ASMEM ? 1 : 2)
 
 }  // namespace
 
-size_t fcn_blk_smem(int k, int threads, bool a_smem) {
-  return sizeof(double) * (size_t)FcnSmem(k, threads / 32, a_smem).total;
-}
+size_t fcn_blk_smem(int k, int threads) { return sizeof(double) * (size_t)FcnSmem(k, threads / 32).total; }
 
 void launch_fcn_solve(cudaStream_t s, const FcnArgs &a) {
   if (a.nunits == 0) return;
   const int k = a.k;
   LK_REQUIRE(k >= 2 && k <= LETKF_B200_MAX_MEMBERS, "fcn solver: need 2 <= k <= 256");
-  // one thread per matrix row in the panel phases
+  // One thread per matrix row in the panel phases and no more: small CTAs, many per SM (k = 64: 28 KB of shared
+  // memory and 2 warps per CTA, 8 CTAs per SM).  Measured on B200 (profiles/README.md): keeping the matrix in
+  // shared memory (one or two CTAs per SM) is 1.4x SLOWER than leaving it in L2 with more CTAs resident, and
+  // CTAs larger than k threads lose to their own barriers.
   const int threads = std::max(64, ((k + 31) / 32) * 32);
-  // the matrix stays in shared memory only while two CTAs still fit on an SM (other units' barriers and
-  // reflector chains then overlap); larger matrices are processed in place in global memory (L2)
-  const bool a_smem = fcn_blk_smem(k, threads, true) <= 110 * 1024;
-  const size_t smem = fcn_blk_smem(k, threads, a_smem);
+  const size_t smem = fcn_blk_smem(k, threads);
   LK_REQUIRE(a.nunits < ((int64_t)1 << 31), "fcn solver: too many units for one launch");
   auto launch = [&](auto kern) {
     LK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<(unsigned)a.nunits, threads, smem, s>>>(a);
   };
-#define LK_FCN_CASE(R)                                   \
-  case R:                                                \
-    if (a_smem)                                          \
-      launch(fcn_blk_kernel<R, true>);                   \
-    else                                                 \
-      launch(fcn_blk_kernel<R, false>);                  \
-    break;
   switch ((k + 31) / 32) {
-    LK_FCN_CASE(1)
-    LK_FCN_CASE(2)
-    LK_FCN_CASE(3)
-    LK_FCN_CASE(4)
-    LK_FCN_CASE(5)
-    LK_FCN_CASE(6)
-    LK_FCN_CASE(7)
-    default:
-      if (a_smem)
-        launch(fcn_blk_kernel<8, true>);
-      else
-        launch(fcn_blk_kernel<8, false>);
-      break;
+    case 1: launch(fcn_blk_kernel<1>); break;
+    case 2: launch(fcn_blk_kernel<2>); break;
+    case 3: launch(fcn_blk_kernel<3>); break;
+    case 4: launch(fcn_blk_kernel<4>); break;
+    case 5: launch(fcn_blk_kernel<5>); break;
+    case 6: launch(fcn_blk_kernel<6>); break;
+    case 7: launch(fcn_blk_kernel<7>); break;
+    default: launch(fcn_blk_kernel<8>); break;
   }
-#undef LK_FCN_CASE
   LK_CUDA(cudaGetLastError());
 }
 
