@@ -517,6 +517,7 @@ static void run_pipeline(letkf_b200_ctx *c, const letkf_b200_var_config *cfg, in
           fa.nanflag = c->nanflag.p;
           fa.mu = (double)mu;
           fa.poles = c->poles.p;
+          fa.qmax = c->counters.p + 3;
           fa.npts_total = npts;
           fa.pt_base = c0;
           fa.level_stride = nsearch;
@@ -586,9 +587,14 @@ static void run_pipeline(letkf_b200_ctx *c, const letkf_b200_var_config *cfg, in
     }
     if (cfg->tune_q && co.transform && !tq_chunk)
       for (int f = 0; f < nfields; ++f) launch_tune_q(s, k, npts, d_var + (int64_t)f * npts * k);  // core:252-278
-    int32_t h_sw[2] = {0, 0};
-    LK_CUDA(cudaMemcpyAsync(h_sw, c->counters.p + 1, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    int32_t h_sw[3] = {0, 0, 0};
+    LK_CUDA(cudaMemcpyAsync(h_sw, c->counters.p + 1, 3 * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
     LK_CUDA(cudaStreamSynchronize(s));
+    // the 32-pole expansion of C^(-1/2) is accurate to < 1e-12 for condition numbers up to 2^27; a unit beyond
+    // that (observation errors ~4 orders of magnitude below the spread) is refused rather than answered badly
+    LK_REQUIRE(h_sw[2] <= 27, "local analysis matrix with condition number above 2^27 (interval index " +
+                                  std::to_string(h_sw[2]) + "): outside the range of the FP64 solve; "
+                                  "LETKF_B200_SOLVER=jacobi handles it");
     stats.max_sweeps = h_sw[0];
     stats.sweeps_sum = h_sw[1];
     LK_REQUIRE(h_sw[0] <= (k == 32 && !c->force_generic ? LK_JACOBI_CAP32 : LK_JACOBI_CAP),

@@ -26,6 +26,7 @@ namespace lk {
 
 constexpr int FCN_NP = 32;    // poles = lanes
 constexpr int FCN_QMAX = 40;  // intervals [1, 2^q], q = 1..QMAX
+constexpr int FCN_QSAFE = 27; // up to here the 32-pole expansion is good to < 1e-12; beyond, the call fails loudly
 // table layout: poles[(q * 2 + 0) * 32 + j] = c_j, poles[(q * 2 + 1) * 32 + j] = beta_j
 
 // interval index for a spectrum inside [a, lmax]

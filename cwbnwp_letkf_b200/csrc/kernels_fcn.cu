@@ -346,6 +346,7 @@ __global__ void __launch_bounds__(256, 2)
     if (lane == 0) {
       s_q = q;
       s_aedge = aedge;
+      if (q > FCN_QSAFE && a.qmax) atomicMax(a.qmax, q);
     }
     pole_pivots(k, d, e, aedge * a.poles[(q * 2 + 1) * FCN_NP + lane], rp, lane);
   }

@@ -144,6 +144,7 @@ __global__ void __launch_bounds__(128, MINB) fcn32_kernel(FcnArgs A) {
     const double g = wmax(dd[lane] + el + er);
     const double aedge = fcn_lower_edge(A.mu);
     const int q = fcn_interval(g, aedge);
+    if (q > FCN_QSAFE && lane == 0 && A.qmax) atomicMax(A.qmax, q);
     cw = sqrt(aedge) * A.poles[(q * 2 + 0) * FCN_NP + lane];
     pole_pivots(K32, dd, ee, aedge * A.poles[(q * 2 + 1) * FCN_NP + lane], rp, lane);
   }

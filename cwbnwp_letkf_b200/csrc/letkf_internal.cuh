@@ -205,6 +205,7 @@ struct FcnArgs {
   const int32_t *unit_pt, *nanflag;
   double mu;            // (k-1)/rho: lower bound of the spectrum
   const double *poles;  // device copy of the pole table
+  int32_t *qmax;        // atomicMax of the interval index q over the units (spectrum inside [a, a 2^q]); may be null
   // transform: var == nullptr skips it.  Point of (unit, level) = pt_base + level*level_stride + unit_pt[unit]
   int64_t npts_total, pt_base, level_stride;
   int nz, nfields;

@@ -222,3 +222,24 @@ def test_two_contexts_do_not_share_state(monkeypatch):
     assert a.launch_count - na0 == 2 * (b.launch_count - nb0)
     a.finalize()
     b.finalize()
+
+
+def test_condition_number_beyond_the_pole_table_is_refused():
+    """The 32-pole expansion of C^(-1/2) is good to < 1e-12 for condition numbers up to 2^27.  Observation errors
+    five orders of magnitude below the ensemble spread put C beyond that: the default FP64 path must fail loudly
+    (status != 0, message names the condition number), not return a degraded analysis."""
+    sc, rng = S.scenario_tiny(k=32)
+    cfg = C.sample_namelist("T")
+    for t in cfg.types:
+        t.err_muti = [1e-5] * 5          # GTS: error x err_muti; radar: the error itself (SURVEY Q12)
+        t.err_rej = [1e9] * 5            # keep the gross-error check from rejecting everything
+    eng = H.LetkfB200(sc.k, True)
+    for o in sc.obs.values():
+        eng.set_obs(o)
+    f = S.make_field(rng, sc.k, sc.xyz_grid, 280.0, 5.0, 1.0)
+    with pytest.raises(H.LetkfError, match="condition number"):
+        eng.analyze(cfg, sc.xyz_grid, f)
+    # the context stays usable
+    st = eng.analyze(C.sample_namelist("T"), sc.xyz_grid, S.make_field(rng, sc.k, sc.xyz_grid, 280.0, 5.0, 1.0))
+    assert st.npts_analysed > 0
+    eng.finalize()
