@@ -39,6 +39,24 @@ __device__ __forceinline__ void apply_q32(const double (&a)[K32], const double *
   }
 }
 
+// Warp sums of three values at once, results in every lane: a transposed butterfly (the first two stages halve
+// what travels) and three broadcasts -- 18 SHFL.32 and 6 DADD instead of 30 and 15, and ONE dependent chain.
+__device__ __forceinline__ void wsum3(double &v0, double &v1, double &v2, int lane) {
+  const bool u16 = lane & 16, u8 = lane & 8;
+  double k0 = u16 ? v2 : v0, k1 = u16 ? 0.0 : v1;
+  const double s0 = u16 ? v0 : v2, s1 = u16 ? v1 : 0.0;
+  k0 += __shfl_xor_sync(FULLF, s0, 16);
+  k1 += __shfl_xor_sync(FULLF, s1, 16);
+  double k = u8 ? k1 : k0;
+  k += __shfl_xor_sync(FULLF, u8 ? k0 : k1, 8);
+  k += __shfl_xor_sync(FULLF, k, 4);
+  k += __shfl_xor_sync(FULLF, k, 2);
+  k += __shfl_xor_sync(FULLF, k, 1);
+  v0 = __shfl_sync(FULLF, k, 0);
+  v1 = __shfl_sync(FULLF, k, 8);
+  v2 = __shfl_sync(FULLF, k, 16);
+}
+
 // sequential (member 0..31) real32 sum of one value per lane, as the oracle defines sum(): the values go
 // through 128 bytes of shared memory (8 broadcast loads) instead of 32 dependent shuffles
 __device__ __forceinline__ float seq_sum32f(float v, float *buf, int lane) {
@@ -89,9 +107,30 @@ __global__ void __launch_bounds__(128, MINB) fcn32_kernel(FcnArgs A) {
     }
   }
 
+  const bool isnan_unit = A.nanflag[unit] != 0;
+  const int64_t upt = A.unit_pt[unit];
+  const double sk = sqrt(31.0);
+  const float ninv = LK_DIV(1.0f, 32.0f);
+  const bool have_field = A.var != nullptr && A.nz > 0 && A.nfields > 0;
+
+  // Two vectors ride along with the tridiagonalisation and come out as Q^T y: b and the first field column.
+  // Their reflector dot products share the step's own reduction (wsum3), so they cost no extra warp sums.
+  double yb = A.bvec[unit * K32 + lane];
+  float xb_first = 0.f;
+  double xmean_first = 0.0, xp_first = 0.0;
+  if (have_field) {
+    xb_first = A.var[(int64_t)lane * A.npts_total + A.pt_base + upt];          // core:228
+    xmean_first = (double)LK_MUL(seq_sum32f(xb_first, fb, lane), ninv);          // core:671 (real32)
+    xp_first = (double)xb_first - xmean_first;                                   // core:672
+  }
+  double yx = xp_first;
+
   // ---- Householder tridiagonalisation, lane = row ----
 #pragma unroll
   for (int j = 0; j < K32 - 2; ++j) {
+    // (Lane j holds the same column in its own row by symmetry, but only to rounding: a reflector whose tau comes
+    // from the row while v comes from the column is not orthogonal when the column is tiny -- measured 3e-7 in
+    // Wa -- so the norm is reduced over the lanes that hold v.)
     const double xj = lane > j ? a[j] : 0.0;
     const double sigma = wsum(xj * xj);
     const double x1 = __shfl_sync(FULLF, a[j], j + 1);
@@ -113,7 +152,11 @@ __global__ void __launch_bounds__(128, MINB) fcn32_kernel(FcnArgs A) {
         p1 = fma(a[l], vw[2 * l], p1);
     }
     double p = lane > j ? (p0 + p1) * tau : 0.0;
-    const double K = 0.5 * tau * wsum(p * v);
+    double r0 = p * v, r1 = v * yb, r2 = v * yx;
+    wsum3(r0, r1, r2, lane);
+    const double K = 0.5 * tau * r0;
+    yb = fma(-(tau * r1), v, yb);  // y <- H_j y
+    yx = fma(-(tau * r2), v, yx);
     const double wv = fma(-K, v, p);
     vw[2 * lane + 1] = wv;
     __syncwarp();
@@ -149,41 +192,28 @@ __global__ void __launch_bounds__(128, MINB) fcn32_kernel(FcnArgs A) {
     pole_pivots(K32, dd, ee, aedge * A.poles[(q * 2 + 1) * FCN_NP + lane], rp, lane);
   }
 
-  const bool isnan_unit = A.nanflag[unit] != 0;
-  const int64_t upt = A.unit_pt[unit];
-  const double sk = sqrt(31.0);
-  const float ninv = LK_DIV(1.0f, 32.0f);
+  // ---- g_b = T^(-1/2) Q^T b ----
+  gb[lane] = yb;
+  __syncwarp();
+  pole_solve(gb, K32, ee, rp, cw, ck, lane);
+  const double gbl = gb[lane];
 
-  // ---- b and the first field together (two independent reflector chains overlap) ----
-  const bool have_field = A.var != nullptr && A.nz > 0 && A.nfields > 0;
-  double gbl;
+  // ---- fields (every level and field that shares these weights) ----
   bool first = true;
   for (int lev = 0; lev < (have_field ? A.nz : 1); ++lev)
     for (int f = 0; f < (have_field ? A.nfields : 1); ++f) {
       const int64_t pt = A.pt_base + (int64_t)lev * A.level_stride + upt;
       float *v = have_field ? A.var + (int64_t)f * A.npts_total * K32 : nullptr;
-      float xb = 0.f;
-      double xmean = 0.0, xp = 0.0;
-      if (have_field) {
-        xb = v[(int64_t)lane * A.npts_total + pt];                         // core:228
+      double xmean = xmean_first, xp = xp_first, y = yx;
+      if (!first && have_field) {
+        const float xb = v[(int64_t)lane * A.npts_total + pt];             // core:228
         xmean = (double)LK_MUL(seq_sum32f(xb, fb, lane), ninv);            // core:671 (real32)
         xp = (double)xb - xmean;                                           // core:672
-      }
-      double y;
-      if (first) {
-        double yy[2] = {A.bvec[unit * K32 + lane], xp};
-        apply_q32<2, true>(a, tt, yy, lane);
-        gb[lane] = yy[0];
-        __syncwarp();
-        pole_solve(gb, K32, ee, rp, cw, ck, lane);  // g_b = T^(-1/2) Q^T b
-        gbl = gb[lane];
-        y = yy[1];
-        first = false;
-      } else {
         double yy[1] = {xp};
         apply_q32<1, true>(a, tt, yy, lane);
         y = yy[0];
       }
+      first = false;
       if (!have_field) break;
       zz[lane] = y;
       __syncwarp();
