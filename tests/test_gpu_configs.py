@@ -243,3 +243,20 @@ def test_condition_number_beyond_the_pole_table_is_refused():
     st = eng.analyze(C.sample_namelist("T"), sc.xyz_grid, S.make_field(rng, sc.k, sc.xyz_grid, 280.0, 5.0, 1.0))
     assert st.npts_analysed > 0
     eng.finalize()
+
+
+@pytest.mark.parametrize("k", [32, 40])
+def test_generic_kernels_forced(k, monkeypatch):
+    """LETKF_B200_GENERIC=1 routes every member count through the generic kernels (SIMT `gram_kernel`, CTA-per-unit
+    solve) -- the path a k = 32 run never takes by default."""
+    monkeypatch.setenv("LETKF_B200_GENERIC", "1")
+    sc, rng = S.scenario_tiny(k=k)
+    cfg = C.sample_namelist("T")
+    eng, orc = _engines(sc)
+    f = S.make_field(rng, k, sc.xyz_grid, 280.0, 5.0, 1.0)
+    err, same, npo, rows = _field_parity(eng, orc, cfg, sc.xyz_grid, f)
+    pts = np.sort(rng.choice(sc.npts, 60, replace=False))
+    worst, analysed, prow = _point_parity(eng, orc, cfg, np.ascontiguousarray(sc.xyz_grid[pts]),
+                                          np.ascontiguousarray(f[:, pts]))
+    _record("generic_forced_k%d" % k, analysed=npo, field_max_rel=err, **{"max_rel_" + kk: v for kk, v in worst.items()})
+    eng.finalize()
