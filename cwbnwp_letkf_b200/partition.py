@@ -135,23 +135,46 @@ def _exchange(send, recv):
             w.wait()
 
 
+_PLANS = {}
+
+
+def _plan(device, world: int, nx: int, ny: int, nxb: int, nyb: int, stagger: int):
+    """Index tensors of every rank's columns on `device`, built once per (decomposition, stagger): xi / yj for the
+    two-step gather of scatter_grid and the flattened (y * nxx + x) indices for the index_copy_ of gather_grid.
+    Rebuilding them per call (numpy tables + a host-to-device copy per peer, variable and direction) cost more
+    than the exchange itself."""
+    key = (str(device), world, nx, ny, nxb, nyb, stagger)
+    p = _PLANS.get(key)
+    if p is None:
+        import torch
+        xk, yk = ("xloc_u" if stagger == 1 else "xloc"), ("yloc_v" if stagger == 2 else "yloc")
+        nxx = nx + (1 if stagger == 1 else 0)
+        p = []
+        for r in range(world):
+            t = local_index_tables(r, world, nx, ny, nxb, nyb)
+            xi = torch.as_tensor(t[xk], device=device)
+            yj = torch.as_tensor(t[yk], device=device)
+            p.append({"xi": xi, "yj": yj, "lx": len(t[xk]), "ly": len(t[yk]),
+                      "flat": (yj[:, None] * nxx + xi[None, :]).reshape(-1)})
+        _PLANS[key] = p
+    return p
+
+
 def scatter_grid(field, k: int, rank: int, world: int, nxb: int = 1, nyb: int = 1, stagger: int = 0):
     """field: torch tensor [m_r, nz, ny(+1), nx(+1)] (this rank's members of the full grid, x fastest).
     Returns var [k, nz, loc_ny, loc_nx] with every member of the columns this rank owns.  stagger: 0 mass,
     1 U (x extent nx+1), 2 V (y extent ny+1), as in letkf_scatter_grid."""
     import torch
-    nz, nyy, nxx = field.shape[1:]
+    m, nz, nyy, nxx = field.shape
     nx, ny = nxx - (1 if stagger == 1 else 0), nyy - (1 if stagger == 2 else 0)
-    xk, yk = ("xloc_u" if stagger == 1 else "xloc"), ("yloc_v" if stagger == 2 else "yloc")
-    tabs = [local_index_tables(r, world, nx, ny, nxb, nyb) for r in range(world)]
-    mine = tabs[rank]
-    lx, ly = len(mine[xk]), len(mine[yk])
-    var = torch.empty((k, nz, ly, lx), dtype=field.dtype, device=field.device)
+    plan = _plan(field.device, world, nx, ny, nxb, nyb, stagger)
+    mine = plan[rank]
+    var = torch.empty((k, nz, mine["ly"], mine["lx"]), dtype=field.dtype, device=field.device)
+    flat = field.reshape(m, nz, nyy * nxx)
     send, recv = {}, {}
     for r in range(world):
-        xi = torch.as_tensor(tabs[r][xk], device=field.device)
-        yj = torch.as_tensor(tabs[r][yk], device=field.device)
-        part = field.index_select(3, xi).index_select(2, yj).contiguous()     # [m_me, nz, ly_r, lx_r]
+        # one gather per peer: [m_me, nz, ly_r * lx_r] in the peer's local column order
+        part = flat.index_select(2, plan[r]["flat"]).view(m, nz, plan[r]["ly"], plan[r]["lx"])
         lo, hi = member_slice(r, world, k)
         if r == rank:
             var[lo:hi] = part
@@ -169,22 +192,18 @@ def gather_grid(var, field, k: int, rank: int, world: int, nxb: int = 1, nyb: in
     import torch
     nz, nyy, nxx = field.shape[1:]
     nx, ny = nxx - (1 if stagger == 1 else 0), nyy - (1 if stagger == 2 else 0)
-    xk, yk = ("xloc_u" if stagger == 1 else "xloc"), ("yloc_v" if stagger == 2 else "yloc")
-    tabs = [local_index_tables(r, world, nx, ny, nxb, nyb) for r in range(world)]
+    plan = _plan(field.device, world, nx, ny, nxb, nyb, stagger)
     lo, hi = member_slice(rank, world, k)
     send, recv = {}, {}
     for r in range(world):
-        lx, ly = len(tabs[r][xk]), len(tabs[r][yk])
         if r == rank:
             recv[r] = var[lo:hi]
         else:
             send[r] = var[slice(*member_slice(r, world, k))].contiguous()
-            recv[r] = torch.empty((hi - lo, nz, ly, lx), dtype=var.dtype, device=var.device)
+            recv[r] = torch.empty((hi - lo, nz, plan[r]["ly"], plan[r]["lx"]), dtype=var.dtype, device=var.device)
     if world > 1:
         _exchange(send, {r: t for r, t in recv.items() if r != rank})
+    out = field.view(hi - lo, nz, nyy * nxx)
     for r in range(world):
-        xi = torch.as_tensor(tabs[r][xk], device=field.device)
-        yj = torch.as_tensor(tabs[r][yk], device=field.device)
-        idx = (yj[:, None] * nxx + xi[None, :]).reshape(-1)
-        field.view(hi - lo, nz, nyy * nxx).index_copy_(2, idx, recv[r].reshape(hi - lo, nz, -1))
+        out.index_copy_(2, plan[r]["flat"], recv[r].reshape(hi - lo, nz, -1))
     return field
