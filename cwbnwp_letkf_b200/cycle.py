@@ -71,9 +71,14 @@ class DeviceCycle:
         xloc, yloc = tab["xloc"], tab["yloc"]
         loc_nx, loc_ny = len(xloc), len(yloc)
         dev = state["ph"].device
+        on_gpu = dev.type == "cuda"              # (CPU tensors + gloo: the world-size-2 test of this loop)
         hstag, vstag = 0, 0                      # core:57-58
         xy = alt = None
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if on_gpu else None
+
+        def mark(i):
+            if on_gpu:
+                ev[i].record()
         for group in group_variables(var_update, self.namelist, batch=self.batch):
             name = group[0]
             key, hs, vs, is_q = VARIABLES[name]
@@ -86,7 +91,7 @@ class DeviceCycle:
                 continue                         # core:66
             hreset, hstag = hstag != hs, hs      # check_coordinate
             vreset, vstag = vstag != vs, vs
-            ev[0].record()
+            mark(0)
             # letkf_scatter_grid of every variable of the group: [k, vnz, ly, lx] each
             cols = []
             for nm in group:
@@ -121,13 +126,14 @@ class DeviceCycle:
             work = torch.empty((len(group), k, npts), dtype=torch.float32, device=dev)
             for gi, c in enumerate(cols):
                 work[gi] = c[:, :, :loc_ny, :loc_nx].reshape(k, npts)
-            ev[1].record()
-            torch.cuda.current_stream().synchronize()    # the library runs on its own stream
+            mark(1)
+            if on_gpu:
+                torch.cuda.current_stream().synchronize()    # the library runs on its own stream
             cfg.tune_q = bool(is_q)                       # letkf_tune_q as the epilogue of the pass (core:252-278)
             eng.set_levels(vnz)
             stats = eng.analyze_dev(cfg, xyz.reshape(-1, 3), work if len(group) > 1 else work[0])
             eng.set_levels(1)
-            ev[2].record()
+            mark(2)
             # letkf_gather_grid
             for gi, (nm, c) in enumerate(zip(group, cols)):
                 c[:, :, :loc_ny, :loc_nx] = work[gi].reshape(k, vnz, loc_ny, loc_nx)
@@ -135,10 +141,11 @@ class DeviceCycle:
                 partition.gather_grid(c, f[:, None] if nm == "MU" else f, k, self.rank, self.world, self.nxb,
                                       self.nyb, stagger=hs)
                 self.log.append((nm, stats))
-            ev[3].record()
-            ev[3].synchronize()
-            self.ms_exchange += ev[0].elapsed_time(ev[1]) + ev[2].elapsed_time(ev[3])
-            self.ms_analysis += stats.ms_total
+            mark(3)
+            if on_gpu:
+                ev[3].synchronize()
+                self.ms_exchange += ev[0].elapsed_time(ev[1]) + ev[2].elapsed_time(ev[3])
+            self.ms_analysis += float(getattr(stats, "ms_total", 0.0))
             del cols, work, xyz
             if after_group is not None:
                 after_group(group)
