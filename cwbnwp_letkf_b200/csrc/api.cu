@@ -51,6 +51,10 @@ struct letkf_b200_ctx {
   DevBuf<unsigned char> C, b, lam, wbar;  // sized in bytes for the working precision
   std::vector<cudaEvent_t> io_ev;         // chunk-granular host IO: [2*i] upload done, [2*i+1] chunk analysed
   CtxShared shared;                       // launch counter, eigensolver scratch (bound per call, CtxBind)
+  // host-sync-free chunk loop of the FP64 path: per-chunk unit / row counts stay on the device, stage events per chunk
+  DevBuf<int32_t> chunk_cnt;
+  DevBuf<int64_t> chunk_rows;
+  std::vector<cudaEvent_t> st_ev;         // 4 per chunk: start, after search + compaction, after Gram, after solve
   // FP64 solve = Householder tridiagonalisation + pole expansion of C^(-1/2) (fcn_common.cuh); the
   // Jacobi eigensolver path stays selectable (LETKF_B200_SOLVER=jacobi) and serves the FP32 build
   bool use_fcn = true;
@@ -134,6 +138,7 @@ extern "C" int letkf_b200_finalize(letkf_b200_ctx *c) {
       if (ev) cudaEventDestroy(ev);
     cudaStreamDestroy(c->stream);
     for (auto &ev : c->io_ev) cudaEventDestroy(ev);
+    for (auto &ev : c->st_ev) cudaEventDestroy(ev);
     if (c->cs_in) {
       cudaStreamDestroy(c->cs_in);
       cudaStreamDestroy(c->cs_out);
@@ -451,7 +456,105 @@ static void run_pipeline(letkf_b200_ctx *c, const letkf_b200_var_config *cfg, in
       LK_CUDA(cudaMemcpy2DAsync(co.h_out + c0, sizeof(float) * npts, d_var + c0, sizeof(float) * npts,
                                 sizeof(float) * nq, io_rows, cudaMemcpyDeviceToHost, c->cs_out));
     };
-    for (int64_t c0 = 0; c0 < nsearch; c0 += chunk) {
+    // FP64 default path: the whole variable is queued without a host synchronisation.  The compaction leaves
+    // the unit count of a chunk on the device; Gram and solve are launched with the chunk size as the grid and
+    // drop the surplus units themselves (TreeViews::nunits_dev).  A stalled host thread (another process polling
+    // the driver, the scheduler) then no longer leaves the GPU idle between chunks -- measured as an occasional
+    // +9 % step whose stage times summed to the normal total.
+    const bool async_chunks = c->use_fcn && sizeof(T) == 8;
+    const int64_t nchunks_all = (nsearch + chunk - 1) / chunk;
+    if (async_chunks) {
+      c->chunk_cnt.ensure(nchunks_all);
+      c->chunk_rows.ensure(nchunks_all);
+      LK_CUDA(cudaMemsetAsync(c->chunk_cnt.p, 0, sizeof(int32_t) * nchunks_all, s));
+      LK_CUDA(cudaMemsetAsync(c->chunk_rows.p, 0, sizeof(int64_t) * nchunks_all, s));
+      while ((int64_t)c->st_ev.size() < 4 * nchunks_all) {
+        cudaEvent_t e;
+        LK_CUDA(cudaEventCreate(&e));
+        c->st_ev.push_back(e);
+      }
+      const bool fast32 = k == 32 && !c->force_generic;
+      c->C.ensure((size_t)chunk * k * k * sizeof(T) + 4096);  // the solve may read (and discard) up to 127 rows past a column
+      c->b.ensure((size_t)chunk * k * sizeof(T));
+      T *C = reinterpret_cast<T *>(c->C.p), *b = reinterpret_cast<T *>(c->b.p);
+      for (int64_t c0 = 0; c0 < nsearch; c0 += chunk) {
+        const int64_t nq = std::min(chunk, nsearch - c0);
+        const int64_t ci = c0 / chunk;
+        cudaEvent_t *ev4 = &c->st_ev[4 * ci];
+        LK_CUDA(cudaEventRecord(ev4[0], s));
+        for (int t = 0; t < tv.ntrees; ++t) launch_search(s, tv.t[t], nq, d_xyz + c0 * 3);
+        launch_count_rows(s, tv, nq, c->p.p);
+        size_t tb = c->cub_tmp.n;
+        LK_CUDA(cub::DeviceSelect::Flagged(c->cub_tmp.p, tb, cit, c->p.p, c->unit_pt.p, c->chunk_cnt.p + ci, (int)nq, s));
+        tb = c->cub_tmp.n;
+        LK_CUDA(cub::DeviceReduce::Sum(c->cub_tmp.p, tb, c->p.p, c->chunk_rows.p + ci, (int)nq, s));
+        launch_counter() += 2;
+        LK_CUDA(cudaEventRecord(ev4[1], s));
+        if (co.p) LK_CUDA(cudaMemcpyAsync(co.p + c0, c->p.p, sizeof(int32_t) * nq, cudaMemcpyDeviceToDevice, s));
+        if (host_io) LK_CUDA(cudaStreamWaitEvent(s, c->io_ev[2 * ci], 0));  // this chunk's fields are in HBM
+        tv.nunits_dev = c->chunk_cnt.p + ci;
+        if (fast32)
+          launch_gram32(s, tv, nq, c->unit_pt.p, (double)mu, reinterpret_cast<double *>(C), reinterpret_cast<double *>(b),
+                        c->nanflag.p);
+        else if (c->force_generic)
+          launch_gram<T>(s, tv, k, nq, c->unit_pt.p, mu, C, b, c->nanflag.p);
+        else if (k % 4 == 0)
+          launch_gram_tma<T>(s, tv, k, nq, c->unit_pt.p, mu, C, b, c->nanflag.p);
+        else
+          launch_gram_dmma<T>(s, tv, k, nq, c->unit_pt.p, mu, C, b, c->nanflag.p);
+        LK_CUDA(cudaEventRecord(ev4[2], s));
+        FcnArgs fa;
+        fa.k = k;
+        fa.nunits = nq;
+        fa.nunits_dev = tv.nunits_dev;
+        fa.C = reinterpret_cast<double *>(C);
+        fa.bvec = reinterpret_cast<const double *>(b);
+        fa.unit_pt = c->unit_pt.p;
+        fa.nanflag = c->nanflag.p;
+        fa.mu = (double)mu;
+        fa.poles = c->poles.p;
+        fa.qmax = c->counters.p + 3;
+        fa.npts_total = npts;
+        fa.pt_base = c0;
+        fa.level_stride = nsearch;
+        fa.nz = nz;
+        fa.nfields = nfields;
+        fa.var = (co.transform && nfields > 0) ? d_var : nullptr;
+        fa.use_rtpp = cfg->use_rtpp;
+        fa.rtpp_alpha = cfg->rtpp_alpha;
+        fa.use_rtps = cfg->use_rtps;
+        fa.rtps_alpha = cfg->rtps_alpha;
+        fa.xa_raw = co.xa_raw;
+        fa.wbar_out = co.wbar ? co.wbar + c0 * k : nullptr;
+        fa.Wa_out = co.Wa ? co.Wa + c0 * (int64_t)k * k : nullptr;
+        if (fast32)
+          launch_fcn32_solve(s, fa);
+        else
+          launch_fcn_solve(s, fa);
+        launch_counter()++;
+        LK_CUDA(cudaEventRecord(ev4[3], s));
+        if (host_io) chunk_out(ci, c0, nq, false);
+      }
+      tv.nunits_dev = nullptr;
+      std::vector<int32_t> h_cnt(nchunks_all);
+      std::vector<int64_t> h_rows(nchunks_all);
+      LK_CUDA(cudaMemcpyAsync(h_cnt.data(), c->chunk_cnt.p, sizeof(int32_t) * nchunks_all, cudaMemcpyDeviceToHost, s));
+      LK_CUDA(cudaMemcpyAsync(h_rows.data(), c->chunk_rows.p, sizeof(int64_t) * nchunks_all, cudaMemcpyDeviceToHost, s));
+      LK_CUDA(cudaStreamSynchronize(s));
+      for (int64_t ci = 0; ci < nchunks_all; ++ci) {
+        stats.npts_analysed += (int64_t)h_cnt[ci] * nz;
+        stats.units += h_cnt[ci];
+        stats.rows += h_rows[ci] * nz;
+        float ms = 0;
+        LK_CUDA(cudaEventElapsedTime(&ms, c->st_ev[4 * ci], c->st_ev[4 * ci + 1]));
+        ms_search += ms;
+        LK_CUDA(cudaEventElapsedTime(&ms, c->st_ev[4 * ci + 1], c->st_ev[4 * ci + 2]));
+        ms_gram += ms;
+        LK_CUDA(cudaEventElapsedTime(&ms, c->st_ev[4 * ci + 2], c->st_ev[4 * ci + 3]));
+        ms_eig += ms;
+      }
+    }
+    for (int64_t c0 = 0; !async_chunks && c0 < nsearch; c0 += chunk) {
       const int64_t nq = std::min(chunk, nsearch - c0);
       const int64_t ci = c0 / chunk;
       LK_CUDA(cudaEventRecord(c->ev[2], s));
@@ -484,8 +587,8 @@ static void run_pipeline(letkf_b200_ctx *c, const letkf_b200_var_config *cfg, in
         const bool fast32 = k == 32 && !c->force_generic;  // warp-per-unit register kernels
         // k = 32 FP64 with one transform per unit and no parity dump: the transform runs in the
         // eigensolver's epilogue and U never leaves the registers
-        const bool use_fcn = c->use_fcn && sizeof(T) == 8;
-        const bool fuse = !use_fcn && fast32 && sizeof(T) == 8 && nz == 1 && co.transform && nfields > 0 && !co.wbar &&
+        // (the FP64 default path never gets here: async_chunks above)
+        const bool fuse = fast32 && sizeof(T) == 8 && nz == 1 && co.transform && nfields > 0 && !co.wbar &&
                           !co.Wa && eig32_can_fuse();
         Xform32Args xargs{c->unit_pt.p, c->nanflag.p, npts, c0, nfields, d_var, cfg->use_rtpp, cfg->rtpp_alpha,
                           cfg->use_rtps, cfg->rtps_alpha, co.xa_raw};
@@ -505,39 +608,7 @@ static void run_pipeline(letkf_b200_ctx *c, const letkf_b200_var_config *cfg, in
         else
           launch_gram<T>(s, tv, k, nunits, c->unit_pt.p, mu, C, b, c->nanflag.p);
         LK_CUDA(cudaEventRecord(c->ev[4], s));
-        if (use_fcn) {
-          // tridiagonalisation + pole expansion: solve, transform of every level / field and the parity dump
-          // in one kernel (fcn_common.cuh); nothing but C, b and the field columns is read or written
-          FcnArgs fa;
-          fa.k = k;
-          fa.nunits = nunits;
-          fa.C = reinterpret_cast<double *>(C);
-          fa.bvec = reinterpret_cast<const double *>(b);
-          fa.unit_pt = c->unit_pt.p;
-          fa.nanflag = c->nanflag.p;
-          fa.mu = (double)mu;
-          fa.poles = c->poles.p;
-          fa.qmax = c->counters.p + 3;
-          fa.npts_total = npts;
-          fa.pt_base = c0;
-          fa.level_stride = nsearch;
-          fa.nz = nz;
-          fa.nfields = nfields;
-          fa.var = (co.transform && nfields > 0) ? d_var : nullptr;
-          fa.use_rtpp = cfg->use_rtpp;
-          fa.rtpp_alpha = cfg->rtpp_alpha;
-          fa.use_rtps = cfg->use_rtps;
-          fa.rtps_alpha = cfg->rtps_alpha;
-          fa.xa_raw = co.xa_raw;
-          fa.wbar_out = co.wbar ? co.wbar + c0 * k : nullptr;
-          fa.Wa_out = co.Wa ? co.Wa + c0 * (int64_t)k * k : nullptr;
-          if (fast32)
-            launch_fcn32_solve(s, fa);
-          else
-            launch_fcn_solve(s, fa);
-          launch_counter()++;
-          LK_CUDA(cudaEventRecord(c->ev[5], s));
-        } else {
+        {
         if (fast32)
           launch_eig32_solve<T>(s, nunits, C, b, lam, wbar, c->counters.p + 1, fuse ? &xargs : nullptr);
         else

@@ -203,7 +203,7 @@ __global__ void __launch_bounds__(256, 2)
   __shared__ double s_aedge;
 
   const int64_t unit = blockIdx.x;
-  if (unit >= a.nunits) return;
+  if (unit >= a.nunits || (a.nunits_dev && unit >= *a.nunits_dev)) return;
   double *Cg = a.C + unit * (int64_t)k * k;
   double *A = Cg;  // processed in place in global memory: L2 resident (rows >= k of a column read the next column)
   const int ld = k;

@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(128, MINB) fcn32_kernel(FcnArgs A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int64_t unit = (int64_t)blockIdx.x * 4 + w;
-  if (unit >= A.nunits) return;
+  if (unit >= A.nunits || (A.nunits_dev && unit >= *A.nunits_dev)) return;
   double *sm = reinterpret_cast<double *>(smem_raw) + (size_t)w * SM_WARP;
   double *vw = sm + SM_VW, *dd = sm + SM_D, *ee = sm + SM_E, *tt = sm + SM_T, *gb = sm + SM_GB, *zz = sm + SM_Z;
   double *ck = sm + SM_CK, *rp = sm + SM_RP, *xs = sm + SM_X;

@@ -41,7 +41,7 @@ __global__ void __launch_bounds__(256)
   __shared__ int s_nan;
 
   const int64_t unit = blockIdx.x;
-  if (unit >= nunits) return;
+  if (unit >= nunits || (tv.nunits_dev && unit >= *tv.nunits_dev)) return;
   const int64_t q = unit_pt[unit];
   const int tid = threadIdx.x;
   const int tx = tid & 15, ty = tid >> 4;
@@ -200,7 +200,7 @@ __global__ void __launch_bounds__(256)
   __shared__ unsigned s_pmask;
 
   const int64_t unit = blockIdx.x;
-  if (unit >= nunits) return;
+  if (unit >= nunits || (tv.nunits_dev && unit >= *tv.nunits_dev)) return;
   const int64_t q = unit_pt[unit];
   const int tid = threadIdx.x, nt = blockDim.x;
   const int warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
@@ -429,7 +429,7 @@ __global__ void __launch_bounds__(NS == 2 ? 288 : 512)
   __shared__ int s_last[kStages];
 
   const int64_t unit = blockIdx.x;
-  if (unit >= nunits) return;
+  if (unit >= nunits || (tv.nunits_dev && unit >= *tv.nunits_dev)) return;
   const int64_t q = unit_pt[unit];
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;

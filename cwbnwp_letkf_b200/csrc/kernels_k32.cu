@@ -22,7 +22,7 @@ __global__ void __launch_bounds__(128)
                        double *__restrict__ C, double *__restrict__ bvec, int32_t *__restrict__ nanflag) {
   const int lane = threadIdx.x & 31;
   const int64_t unit = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
-  if (unit >= nunits) return;
+  if (unit >= nunits || (tv.nunits_dev && unit >= *tv.nunits_dev)) return;
   const bool wn = gram32_unit(tv, unit_pt[unit], mu, C + unit * 1024, 32, bvec + unit * 32, lane);
   if (lane == 0) nanflag[unit] = wn ? 1 : 0;
 }

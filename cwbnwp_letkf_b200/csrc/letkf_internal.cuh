@@ -131,6 +131,10 @@ struct TreeView {
 struct TreeViews {
   int ntrees;
   int weight_function;
+  // Number of analysis units of the current chunk as the compaction left it ON THE DEVICE (null: the launch
+  // argument is exact).  Lets the host queue a chunk's Gram / solve kernels with the chunk size as the grid,
+  // without waiting for the count: units beyond *nunits_dev exit at once.
+  const int32_t *nunits_dev;
   TreeView t[LETKF_B200_MAX_TYPES];
 };
 
@@ -205,6 +209,7 @@ struct FcnArgs {
   const int32_t *unit_pt, *nanflag;
   double mu;            // (k-1)/rho: lower bound of the spectrum
   const double *poles;  // device copy of the pole table
+  const int32_t *nunits_dev;  // device-side unit count (null: nunits is exact), see TreeViews
   int32_t *qmax;        // atomicMax of the interval index q over the units (spectrum inside [a, a 2^q]); may be null
   // transform: var == nullptr skips it.  Point of (unit, level) = pt_base + level*level_stride + unit_pt[unit]
   int64_t npts_total, pt_base, level_stride;
