@@ -82,11 +82,14 @@ class ClockSampler:
 
     def __init__(self, index: int):
         self.index, self.rows, self.proc = index, [], None
+        self.period_ms = int(os.environ.get("LETKF_BENCH_SMI_MS", "200"))   # the recipe's clocks line: -lms 200
 
     def start(self):
+        if os.environ.get("LETKF_BENCH_NO_SMI"):   # experiment knob: shows what the in-run polling itself costs
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                          "--format=csv,noheader,nounits", "-lms", str(self.period_ms)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
