@@ -33,8 +33,9 @@ def main():
         launches = json.load(open(summ))
         plain = json.load(open(os.path.join(OUT, "%s_%s_plain.json" % (tag, case))))
         k = plain["config"]["members"]
-        units = plain["points_analysed"]              # one pipeline chunk in these small cases
-        npts = int(round(plain["points_analysed"] / max(plain["analysed_fraction"], 1e-9)))
+        # one captured launch = one pipeline chunk: at most 2^18 grid points (the k = 32 case has five chunks)
+        npts = min(int(round(plain["points_analysed"] / max(plain["analysed_fraction"], 1e-9))), 1 << 18)
+        units = min(plain["points_analysed"], int(round(npts * plain["analysed_fraction"])))
         rows = plain["rows_per_analysed_point"]
         alg = {"gram": (4 * k + 8) * rows + 8 * k * k + 8 * k,           # gathered rows + C, b written
                "solve": 8 * k * k + 8 * k + 8 * k,                      # C, b read + xb in / xa out (one field)
