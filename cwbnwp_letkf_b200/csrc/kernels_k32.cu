@@ -10,6 +10,8 @@
 // transform32: xa = xb_mean + xb'.wbar + sqrt(k-1) U Lambda^(-1/2) U^T xb' with lane i holding row i
 // of U (the layout eig32 writes), one transposed butterfly for U^T xb' and a shared-memory
 // broadcast for the second product; RTPP/RTPS exactly as kernels_xform.cu.
+#include <cstdlib>
+
 #include "gram32.cuh"
 #include "xform32.cuh"
 
@@ -17,7 +19,8 @@ namespace lk {
 
 constexpr unsigned FULLM = 0xffffffffu;
 
-__global__ void __launch_bounds__(128)
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB)
     gram32_dmma_kernel(TreeViews tv, int64_t nunits, const int32_t *__restrict__ unit_pt, double mu,
                        double *__restrict__ C, double *__restrict__ bvec, int32_t *__restrict__ nanflag) {
   const int lane = threadIdx.x & 31;
@@ -30,7 +33,19 @@ __global__ void __launch_bounds__(128)
 void launch_gram32(cudaStream_t s, const TreeViews &tv, int64_t nunits, const int32_t *unit_pt, double mu,
                    double *C, double *b, int32_t *nanflag) {
   if (nunits == 0) return;
-  gram32_dmma_kernel<<<(unsigned)((nunits + 3) / 4), 128, 0, s>>>(tv, nunits, unit_pt, mu, C, b, nanflag);
+  // resident CTAs per SM the kernel is compiled for: 6 = 80 registers (no cap), 7 = 72, 8 = 64 (spills).
+  // Measured on a 225 x 225 x 50 grid: 161.6 / 155.4 / 160.8 ms -- 28 warps per SM at 72 registers is the best.
+  static const int minb = [] {
+    const char *e = getenv("LETKF_B200_GRAM32_MINB");
+    return e ? atoi(e) : 7;
+  }();
+  const unsigned grid = (unsigned)((nunits + 3) / 4);
+  if (minb == 8)
+    gram32_dmma_kernel<8><<<grid, 128, 0, s>>>(tv, nunits, unit_pt, mu, C, b, nanflag);
+  else if (minb == 7)
+    gram32_dmma_kernel<7><<<grid, 128, 0, s>>>(tv, nunits, unit_pt, mu, C, b, nanflag);
+  else
+    gram32_dmma_kernel<6><<<grid, 128, 0, s>>>(tv, nunits, unit_pt, mu, C, b, nanflag);
   launch_counter()++;
   LK_CUDA(cudaGetLastError());
 }
