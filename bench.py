@@ -214,7 +214,10 @@ def stage_report(stats, k: int, fma64: float, members: int):
             tab = {}            # the committed capture is from another tree: its numbers are not this run's
     except Exception:
         tab = {}
-    per_launch_units = min(units, 1 << 18)
+    # units one launch processes = one pipeline chunk: at most 2^18 grid points, fewer for large k (the library sizes
+    # chunks against a 40 GB budget for the per-unit matrices, api.cu pick_chunk)
+    chunk_est = max(1024, min(1 << 18, int((40 << 30) / (16 + (k * k + 3 * k) * 8 + 8192))))
+    per_launch_units = min(units, chunk_est)
     for s_ in ("search", "gram", "solve"):
         t_ = tab.get(s_)
         stage[s_]["traffic_bytes_per_launch"] = t_["bytes_per_unit"] * per_launch_units if t_ else None
