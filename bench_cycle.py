@@ -43,8 +43,9 @@ def make_geo(nx, ny, dx):
         return ((np.arange(n, dtype=np.float64) - (n - 1) / 2 + off) * dx).astype(np.float32)
     geo = {}
     for sfx, (nxx, nyy, ox, oy) in {"": (nx, ny, 0.0, 0.0), "_u": (nx + 1, ny, 0.0, 0.0), "_v": (nx, ny + 1, 0.0, 0.0)}.items():
-        xs = axis(nx, 0.0) if nxx == nx else axis(nx + 1, 0.0) - np.float32(0.5 * dx)
-        ys = axis(ny, 0.0) if nyy == ny else axis(ny + 1, 0.0) - np.float32(0.5 * dx)
+        # nx + 1 staggered points centred on the same centre sit exactly half a cell off the nx mass points
+        xs = axis(nx, 0.0) if nxx == nx else axis(nx + 1, 0.0)
+        ys = axis(ny, 0.0) if nyy == ny else axis(ny + 1, 0.0)
         X, Y = np.meshgrid(xs, ys, indexing="ij")
         geo["xlon" + sfx], geo["xlat" + sfx] = X.astype(np.float32), Y.astype(np.float32)
     span = max(nx, ny) * dx
