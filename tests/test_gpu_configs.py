@@ -260,3 +260,38 @@ def test_generic_kernels_forced(k, monkeypatch):
                                           np.ascontiguousarray(f[:, pts]))
     _record("generic_forced_k%d" % k, analysed=npo, field_max_rel=err, **{"max_rel_" + kk: v for kk, v in worst.items()})
     eng.finalize()
+
+
+def test_two_contexts_on_two_devices(monkeypatch):
+    """One process driving two GPUs (the header's threading note): a context per device, calls interleaved.  The
+    Jacobi path at k = 192 is used because it is the one with per-context scratch memory; results must be identical
+    on both devices and unaffected by the interleaving.  Needs two GPUs (skipped otherwise)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    monkeypatch.setenv("LETKF_B200_SOLVER", "jacobi")
+    k = 192
+    sc, rng = S.scenario_tiny(k=k, nx=8, ny=5, nz=4)
+    cfg = C.sample_namelist("T")
+    xb = S.make_field(rng, k, sc.xyz_grid, 280.0, 5.0, 1.0)
+    a, b = H.LetkfB200(k, True, 0), H.LetkfB200(k, True, 1)
+    for o in sc.obs.values():
+        a.set_obs(o)
+        b.set_obs(o)
+    ra = a.letkf_weights(cfg, sc.xyz_grid, xb)
+    rb = b.letkf_weights(cfg, sc.xyz_grid, xb)
+    ra2 = a.letkf_weights(cfg, sc.xyz_grid, xb)
+    for x, y, z in zip(ra, rb, ra2):
+        assert np.array_equal(x, y) and np.array_equal(x, z)
+    monkeypatch.setenv("LETKF_B200_SOLVER", "fcn")
+    c0, c1 = H.LetkfB200(k, True, 0), H.LetkfB200(k, True, 1)
+    for o in sc.obs.values():
+        c0.set_obs(o)
+        c1.set_obs(o)
+    f0 = S.make_field(rng, k, sc.xyz_grid, 280.0, 5.0, 1.0)
+    f1 = f0.copy()
+    s0 = c0.analyze(cfg, sc.xyz_grid, f0)
+    s1 = c1.analyze(cfg, sc.xyz_grid, f1)
+    assert s0.npts_analysed == s1.npts_analysed > 0 and np.array_equal(f0, f1)
+    for e in (a, b, c0, c1):
+        e.finalize()
