@@ -30,6 +30,22 @@ from . import partition
 from .driver import G, VARIABLES, Projection, group_variables
 
 
+def lonlat_to_xy_device(proj: Projection, lon, lat):
+    """module_projection.f90:37-50 on device tensors (real32, the constants of proj_init evaluated once on the host
+    exactly as driver.Projection does).  The transcendental functions are the device library's, so x, y can differ
+    from the host evaluation in the last bits (~1 m at rh ~ 1e7 m) -- the Fortran source does not define those bits
+    either (compiler libm); DeviceCycle uses it only with device_projection=True and defaults to the host
+    projection so that parity with the letkf_driver mirror stays bit-exact."""
+    import torch
+    f32 = torch.float32
+    lon, lat = lon.to(f32), lat.to(f32)
+    half, pi, d2r = 0.5, float(proj._pi), float(proj._d2r)
+    cot = 1.0 / torch.tan(half * (half * pi + lat * d2r))
+    rh = float(np.float32(proj.earthradius)) * float(proj.f) * torch.exp(float(proj.n) * torch.log(cot))
+    dlon = float(proj.n) * (lon * d2r - float(proj.lon0))
+    return rh * torch.sin(dlon), float(proj.rh0) - rh * torch.cos(dlon)
+
+
 class DeviceCycle:
     """``run(state, geo, var_update)`` == the ``update`` loop of letkf_driver for this rank, fields in HBM.
 
@@ -40,8 +56,9 @@ class DeviceCycle:
     """
 
     def __init__(self, eng, namelist: Callable[[str], object], proj: Projection, rank: int = 0, world: int = 1,
-                 nxb: int = 1, nyb: int = 1, batch: bool = True):
+                 nxb: int = 1, nyb: int = 1, batch: bool = True, device_projection: bool = False):
         self.eng, self.namelist, self.proj = eng, namelist, proj
+        self.device_projection = device_projection   # proj%lonlat_to_xy (core:211) on the device, see lonlat_to_xy_device
         self.rank, self.world, self.nxb, self.nyb, self.batch = rank, world, nxb, nyb, batch
         self.log = []
         self.ms_exchange = 0.0
@@ -106,9 +123,14 @@ class DeviceCycle:
                 yj = tab["yloc_v"] if hs == 2 else yloc
                 lat = geo["xlat" + sfx][np.ix_(xi, yj)]
                 lon = geo["xlon" + sfx][np.ix_(xi, yj)]
-                x, y = self.proj.lonlat_to_xy(lon[:loc_nx, :loc_ny], lat[:loc_nx, :loc_ny])
-                xy = (torch.from_numpy(np.ascontiguousarray(x.T)).to(dev),
-                      torch.from_numpy(np.ascontiguousarray(y.T)).to(dev))        # [loc_ny, loc_nx]
+                if self.device_projection and isinstance(self.proj, Projection):
+                    dlon = torch.from_numpy(np.ascontiguousarray(lon[:loc_nx, :loc_ny].T)).to(dev)
+                    dlat = torch.from_numpy(np.ascontiguousarray(lat[:loc_nx, :loc_ny].T)).to(dev)
+                    xy = lonlat_to_xy_device(self.proj, dlon, dlat)                  # [loc_ny, loc_nx]
+                else:
+                    x, y = self.proj.lonlat_to_xy(lon[:loc_nx, :loc_ny], lat[:loc_nx, :loc_ny])
+                    xy = (torch.from_numpy(np.ascontiguousarray(x.T)).to(dev),
+                          torch.from_numpy(np.ascontiguousarray(y.T)).to(dev))        # [loc_ny, loc_nx]
             if alt is None or vreset:            # core:189-206
                 if vs == -1:
                     h = np.asarray(geo["hgt"], np.float32)[np.ix_(xloc, yloc)]

@@ -59,6 +59,19 @@ def test_mean_height_on_tensors_equals_the_numpy_restatement():
         assert np.array_equal(np.transpose(got, (2, 1, 0)), ref)
 
 
+def test_projection_on_tensors_agrees_with_the_host_projection_to_real32_rounding():
+    from _driver_case import PROJ
+    proj = D.Projection(**PROJ)
+    rng = np.random.default_rng(4)
+    lon = (120.5 + rng.uniform(-4, 4, (40, 30))).astype(np.float32)
+    lat = (23.5 + rng.uniform(-4, 4, (40, 30))).astype(np.float32)
+    x, y = proj.lonlat_to_xy(lon, lat)
+    xt, yt = CY.lonlat_to_xy_device(proj, torch.from_numpy(lon), torch.from_numpy(lat))
+    # rh ~ 1e7 m in real32: one ulp is ~1 m; the two libm implementations may differ by a few
+    assert np.abs(xt.numpy() - x).max() < 8.0 and np.abs(yt.numpy() - y).max() < 8.0
+    assert xt.dtype == torch.float32 and np.abs(x).max() > 1e5
+
+
 def _worker(rank, world, port, out):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
